@@ -1,0 +1,149 @@
+"""Host logic of xhistogram_b200.core (axis/broadcast/edges/density/dtype policy) on CPU.
+
+The one native call (`core._desc_call` -> xh_hist) is replaced by the oracle's block kernel so that
+everything around it is exercised without a GPU.  The real CUDA path is covered by the `-m gpu`
+tests, which run the same cases with nothing patched."""
+import numpy as np
+import pytest
+
+from oracle import hist_oracle as O
+from tests.conftest import assert_hist_equal, golden_case
+from tests.golden.cases import CASES
+from xhistogram_b200 import core
+
+
+def _oracle_desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing):
+    def full(a, stride):
+        a = np.asarray(a)
+        assert a.flags.c_contiguous and a.shape[1] == N
+        if stride == 0:
+            assert a.shape[0] == 1
+            return np.broadcast_to(a, (M, N))
+        assert stride == N and a.shape[0] == M
+        return a
+    data = [full(a, s) for a, s in zip(arrs, strides)]
+    assert all(a.dtype == data[0].dtype for a in data) and data[0].dtype in (np.float32, np.float64)
+    ww = None if w is None else full(w, wstride)
+    B = int(np.prod([len(b) - 1 for b in bins]))
+    return O.block_bincount(data, [np.asarray(b, dtype=np.float64) for b in bins], ww).reshape(M, B)
+
+
+@pytest.fixture
+def patched(monkeypatch):
+    monkeypatch.setattr(core, "_desc_call", _oracle_desc_call)
+    monkeypatch.setattr(core, "_minmax", lambda a: (float(np.min(a)), float(np.max(a))))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_frontend_reproduces_golden(patched, golden, name):
+    args, kwargs = CASES[name]()
+    h_ref, edges_ref, _ = golden_case(golden, name)
+    h, edges = core.histogram(*args, **kwargs)
+    for e, er in zip(edges, edges_ref):
+        assert e.dtype == er.dtype and np.array_equal(e, er)
+    assert_hist_equal(h, h_ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("block_size", [None, 1, 2, "auto", 5])
+def test_block_size_is_accepted_and_irrelevant(patched, block_size):
+    x = np.random.default_rng(0).standard_normal((5, 20))
+    bins = np.linspace(-4, 4, 10)
+    h, _ = core.histogram(x, bins=bins, axis=1, block_size=block_size)
+    want = np.stack([np.histogram(x[i], bins=bins)[0] for i in range(5)])
+    assert np.array_equal(h, want)
+
+
+def test_shapes_for_every_axis_choice(patched):              # reference test_core.py:231-273
+    from itertools import combinations
+    b = np.random.default_rng(1).standard_normal((3, 4, 5, 6))
+    bins = np.linspace(-4, 4, 27)
+    assert core.histogram(b, bins=bins)[0].shape == (26,)
+    for axis in [(0, 1, 2, 3), (0, 1, 3, 2), (3, 2, 1, 0), (3, 2, 0, 1)]:
+        assert core.histogram(b, bins=bins, axis=axis)[0].shape == (26,)
+    for axis in list(range(4)) + list(range(-1, -5, -1)):
+        shape = list(b.shape); del shape[axis]
+        assert core.histogram(b, bins=bins, axis=axis)[0].shape == tuple(shape) + (26,)
+    for i, j in combinations(range(4), 2):
+        keep = tuple(b.shape[k] for k in range(4) if k not in (i, j))
+        assert core.histogram(b, bins=bins, axis=(i, j))[0].shape == keep + (26,)
+
+
+def test_density_integrates_to_one_per_row(patched):          # reference test_core.py:66-69 and issue #51
+    r = np.random.default_rng(2)
+    x = r.standard_normal((4, 300)); x[1, :50] = np.nan
+    bins = np.linspace(-4, 4, 10)
+    h, _ = core.histogram(x, bins=bins, axis=1, density=True)
+    np.testing.assert_allclose((h * np.diff(bins)).sum(axis=1), 1.0)
+
+
+def test_three_variable_density(patched):
+    r = np.random.default_rng(3)
+    args = [r.standard_normal(300) for _ in range(3)]
+    bins = [np.linspace(-4, 4, n) for n in (10, 11, 10)]
+    h, _ = core.histogram(*args, bins=bins, density=True)
+    want, _ = np.histogramdd(np.stack(args, -1), bins=bins, density=True)
+    np.testing.assert_allclose(h, want)
+
+
+def test_weight_row_broadcast_is_passed_with_stride_zero(monkeypatch):
+    seen = {}
+
+    def spy(arrs, strides, w, wstride, *rest):
+        seen["wstride"], seen["wshape"] = wstride, w.shape
+        return _oracle_desc_call(arrs, strides, w, wstride, *rest)
+
+    monkeypatch.setattr(core, "_desc_call", spy)
+    x = np.random.default_rng(4).standard_normal((5, 20))
+    core.histogram(x, bins=np.linspace(-4, 4, 10), axis=1, weights=2 * np.ones((1, 20)))
+    assert seen == {"wstride": 0, "wshape": (1, 20)}
+
+
+@pytest.mark.parametrize("bins_in,n,ok", [
+    (10, 1, True), ("auto", 2, True), (np.linspace(-4, 4, 10), 2, True), ([10], 1, True),
+    ([10, "auto", np.linspace(0, 1, 3)], 3, True), ([np.linspace(0, 1, 3)], 2, False), (None, 1, False),
+    ([np.linspace(0, 1, 3)] * 2, 1, False)])
+def test_bins_formatting(bins_in, n, ok):                     # reference test_core.py:316-340
+    if ok:
+        assert len(core._ensure_correctly_formatted_bins(bins_in, n)) == n
+    else:
+        with pytest.raises((ValueError, TypeError)):
+            core._ensure_correctly_formatted_bins(bins_in, n)
+
+
+@pytest.mark.parametrize("range_in,n,expected", [
+    ((0, 1), 1, [(0, 1)]), ((0, 1), 2, [(0, 1), (0, 1)]), ([(0, 1), (0, 1)], 2, [(0, 1), (0, 1)]),
+    ([(0,)], 1, None), ([(0, 1)], 2, None), ([(0, 1), (0, 1)], 1, None)])
+def test_range_formatting(range_in, n, expected):             # reference test_core.py:343-362
+    if expected is not None:
+        assert core._ensure_correctly_formatted_range(range_in, n) == expected
+    else:
+        with pytest.raises(ValueError):
+            core._ensure_correctly_formatted_range(range_in, n)
+
+
+def test_errors(patched):
+    x = np.zeros((3, 4))
+    with pytest.raises(ValueError, match="bins must be provided"):
+        core.histogram(x)
+    with pytest.raises(AssertionError):
+        core.histogram(x, bins=3, range=(0, 1), axis=2)
+    with pytest.raises(ValueError):
+        core.histogram(x, np.zeros((5, 4)), bins=3, range=(0, 1))       # not broadcastable
+    with pytest.raises(TypeError):
+        core.histogram(x, bins="auto", weights=np.ones_like(x))         # numpy: estimators do not take weights
+    with pytest.raises(ValueError):
+        core.histogram(x, bins=np.array([0.0, 2.0, 1.0]))               # edges must increase
+    with pytest.raises(TypeError):
+        core.histogram(np.array(["2000-01-01"], dtype="datetime64[D]"), bins=np.array(["1999-01-01", "2001-01-01"], dtype="datetime64[D]"))
+
+
+def test_integer_and_bool_data(patched):
+    r = np.random.default_rng(5)
+    xi = r.integers(-5, 6, 400).astype(np.int32)
+    bins = np.linspace(-5, 5, 11)
+    assert np.array_equal(core.histogram(xi, bins=bins)[0], np.histogram(xi, bins=bins)[0])
+    xb = r.integers(0, 2, 100).astype(bool)
+    assert np.array_equal(core.histogram(xb, bins=2, range=(0, 1))[0], np.histogram(xb, bins=2, range=(0, 1))[0])
+    big = np.array([2**60 + 1], dtype=np.int64)
+    with pytest.raises(TypeError):
+        core.histogram(big, bins=np.array([0.0, 2.0**61]))

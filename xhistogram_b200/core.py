@@ -1,0 +1,411 @@
+"""Numpy-level API: drop-in for ``xhistogram.core.histogram`` on the B200 hot path.
+
+Same signature, argument meaning and error behaviour as the reference front-end
+(xhistogram/core.py:250-466); the O(samples) work — digitize, joint index, bincount
+(reference core.py:73-247) — is one CUDA launch per block behind ``libxhist_b200.so``
+(C-ABI in include/xhist_b200.h).  Everything kept in Python here is O(#bins) or metadata:
+axis normalisation, broadcasting bookkeeping, bin-edge resolution, the density divide.
+
+Inputs may be numpy arrays (staged through a pipelined host->device copy), ``DeviceArray``s or
+any ``__cuda_array_interface__`` object (device-resident, no copy), or dask arrays (the
+reference's ``blockwise(_bincount) + sum`` scheme, with ``_bincount`` running on the GPU).
+
+Differences from the reference, all documented in DESIGN.md:
+* ``block_size`` is a hint with no effect on results or on the GPU launch (in the reference it
+  only bounds a host temporary, core.py:86-134); the reference's ``"auto"`` ZeroDivisionError for
+  flat inputs above 1e7 samples (core.py:114-117) is not reproduced;
+* ``density=True`` with three or more variables works (the reference raises on numpy >= 1.24,
+  core.py:454) and equals ``np.histogramdd(density=True)``;
+* ``bins=<int>`` finds the data range with a device min/max reduction instead of a host pass.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+from collections.abc import Iterable
+
+import numpy as np
+
+from . import _cabi
+from .device import DeviceArray, as_device_view, is_device_array
+
+_range = range
+
+__all__ = ["histogram"]
+
+
+# --------------------------------------------------------------------------------------------
+# argument formatting (reference: core.py:37-70)
+# --------------------------------------------------------------------------------------------
+def _ensure_correctly_formatted_bins(bins, N_expected):
+    if bins is None:
+        raise ValueError("bins must be provided")
+    if isinstance(bins, (int, str, np.ndarray)):
+        bins = N_expected * [bins]
+    if len(bins) == N_expected:
+        return bins
+    raise ValueError("The number of bin definitions doesn't match the number of args")
+
+
+def _ensure_correctly_formatted_range(range_, N_expected):
+    if range_ is None:
+        return N_expected * [range_]
+    nested = all(isinstance(i, Iterable) for i in range_)
+    if len(range_) == 2 and not nested:
+        return N_expected * [range_]
+    if N_expected != len(range_):
+        raise ValueError("The number of ranges doesn't match the number of args")
+    if all(len(x) == 2 for x in range_):
+        return range_
+    raise ValueError(
+        "range should be provided as (lower_range, upper_range). In the "
+        "case of multiple args, range should be a list of such tuples"
+    )
+
+
+def _is_dask(a):
+    return a is not None and type(a).__module__.split(".")[0] == "dask"
+
+
+# --------------------------------------------------------------------------------------------
+# dtype policy for the device compare
+# --------------------------------------------------------------------------------------------
+def _as_float_data(a):
+    """Host array -> float32/float64 with numpy's comparison semantics preserved exactly.
+
+    numpy promotes data and float edges to a common float type before searchsorted; float16 and
+    integers up to 32 bits are exact in that type.  64-bit integers are accepted when the cast to
+    float64 is lossless for this array; anything else (datetime64, complex, object) is refused —
+    there is no CPU fallback to hide it.
+    """
+    dt = a.dtype
+    if dt == np.float32 or dt == np.float64:
+        return a
+    if dt == np.float16:
+        return a.astype(np.float32)
+    if dt == np.bool_ or (dt.kind in "iu" and dt.itemsize <= 4):
+        return a.astype(np.float64)
+    if dt.kind in "iu":
+        f = a.astype(np.float64)
+        if not np.array_equal(f.astype(dt), a):
+            raise TypeError("64-bit integer data beyond 2**53 cannot be binned exactly on the GPU path")
+        return f
+    if dt.kind == "f":  # longdouble
+        return a.astype(np.float64)
+    raise TypeError(f"unsupported data dtype {dt} for the B200 histogram path (float and integer data only)")
+
+
+def _as_float_weights(w):
+    if w.dtype == np.float32 or w.dtype == np.float64:
+        return w
+    if w.dtype.kind in "biuf":
+        return w.astype(np.float64)  # np.bincount casts weights to double (reference core.py:81)
+    raise TypeError(f"unsupported weights dtype {w.dtype}")
+
+
+def _xh_dtype(dt):
+    return _cabi.XH_F32 if np.dtype(dt) == np.float32 else _cabi.XH_F64
+
+
+# --------------------------------------------------------------------------------------------
+# bin edges (reference: core.py:383-388 -> np.histogram_bin_edges)
+# --------------------------------------------------------------------------------------------
+def _minmax(a):
+    """(min, max) of a host or device array through the device reduction (NaN if any NaN, like numpy)."""
+    mn, mx = C.c_double(), C.c_double()
+    if is_device_array(a):
+        ptr, shape, dt, dev = as_device_view(a)
+        n, mem = int(np.prod(shape, dtype=np.int64)), _cabi.XH_DEVICE
+    else:
+        a = np.ascontiguousarray(a)
+        ptr, dt, dev, n, mem = a.ctypes.data, a.dtype, _default_device(), a.size, _cabi.XH_HOST
+    _cabi.check(_cabi.lib().xh_minmax(dev, ptr, _xh_dtype(dt), mem, n, C.byref(mn), C.byref(mx)), "xh_minmax")
+    return mn.value, mx.value
+
+
+def _resolve_edges(a, bins, range_, weights):
+    """Bin edges of one variable, identical to ``np.histogram_bin_edges(a, bins, range, weights)``."""
+    device = is_device_array(a)
+    dt = as_device_view(a)[2] if device else a.dtype
+    size = int(np.prod(as_device_view(a)[1], dtype=np.int64)) if device else a.size
+    if isinstance(bins, str):
+        if device:
+            raise TypeError("string bin estimators need host data; pass explicit bins or an int for device arrays")
+        return np.histogram_bin_edges(a, bins=bins, range=range_, weights=weights)
+    if np.ndim(bins) == 0 and range_ is None and size > 0 and np.dtype(dt).kind == "f" and np.dtype(dt).itemsize in (4, 8):
+        # integer bin count without a range: only min/max of the data matter; take them on the device
+        mn, mx = _minmax(a)
+        probe = np.array([mn, mx], dtype=dt)
+        return np.histogram_bin_edges(probe, bins=bins)
+    if device:
+        probe = np.zeros(1, dtype=dt)
+        return np.histogram_bin_edges(probe, bins=bins, range=range_)
+    if np.ndim(bins) == 0 and range_ is None:
+        return np.histogram_bin_edges(a, bins=bins, range=range_)  # non-float dtype: numpy's own pass
+    probe = np.zeros(1 if size else 0, dtype=dt)
+    return np.histogram_bin_edges(probe, bins=bins, range=range_)
+
+
+# --------------------------------------------------------------------------------------------
+# the seam: one block -> one C-ABI call (reference: _bincount, core.py:197-247)
+# --------------------------------------------------------------------------------------------
+_default_dev = 0
+_debug_flags = 0   # XH_FLAG_FORCE_* bits OR-ed into every call (tests exercise each kernel path with them)
+
+
+class debug_flags:
+    """Context manager: force a kernel path (``_cabi.XH_FLAG_FORCE_GLOBAL/SEARCH/WINDOW``) for the calls inside."""
+
+    def __init__(self, flags):
+        self.flags = int(flags)
+
+    def __enter__(self):
+        global _debug_flags
+        self._old, _debug_flags = _debug_flags, self.flags
+        return self
+
+    def __exit__(self, *exc):
+        global _debug_flags
+        _debug_flags = self._old
+
+
+def _default_device():
+    return _default_dev
+
+
+def set_default_device(device: int):
+    """CUDA ordinal used for host inputs (device inputs run where they live)."""
+    global _default_dev
+    _default_dev = int(device)
+
+
+def _rows_view(a, axis, full):
+    """(2-D C-contiguous host array or single row, row_stride, M, N) for the (kept, reduced) layout."""
+    if full:
+        flat = np.ascontiguousarray(a).reshape(1, -1)
+        return flat, flat.shape[1], 1, flat.shape[1]
+    nd = a.ndim
+    kept = [i for i in _range(nd) if i not in axis]
+    moved = np.transpose(a, kept + list(axis))          # np.moveaxis(a, axis, range(-len(axis), 0)), core.py:218-219
+    M = int(np.prod([a.shape[i] for i in kept], dtype=np.int64))
+    N = int(np.prod([a.shape[i] for i in axis], dtype=np.int64))
+    if M > 1 and all(moved.strides[i] == 0 or moved.shape[i] == 1 for i in _range(len(kept))):
+        # broadcast over every kept axis (e.g. weights of shape (1, ncols)): pass one row, stride 0
+        row = np.ascontiguousarray(moved[(0,) * len(kept)]).reshape(1, N)
+        return row, 0, M, N
+    return np.ascontiguousarray(moved).reshape(M, N), N, M, N
+
+
+def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, block_size=None,
+              _devices=None, _flags=0, _timing=None):
+    """GPU replacement of the reference's ``_bincount`` (core.py:197-247).
+
+    Same contract: ``all_arrays`` are mutually broadcast arrays of identical shape (weights last
+    when ``weights`` is true), ``bins`` a list of 1-D edge arrays; returns an array of shape
+    ``kept_axes_shape (with 1 for every reduced axis) + (nbins_1, ..., nbins_K)``, int64 without
+    weights and float64 with.  It is what dask's ``blockwise`` maps over chunks, so it is
+    re-entrant (the native library serialises per device).
+    """
+    all_arrays = list(all_arrays)
+    a0 = all_arrays[0]
+    device_inputs = is_device_array(a0)
+    shape = as_device_view(a0)[1] if device_inputs else a0.shape
+    nd = len(shape)
+    full = (axis is None) or (set(axis) == set(_range(nd)))
+    kept_axes_shape = (1,) * nd if full else tuple(shape[i] if i not in axis else 1 for i in _range(nd))
+    w = all_arrays.pop() if weights else None
+    nbins = tuple(len(b) - 1 for b in bins)
+
+    if device_inputs:
+        views = [as_device_view(a) for a in all_arrays]
+        wview = as_device_view(w) if w is not None else None
+        for v in views + ([wview] if wview else []):
+            if v[1] != shape:
+                raise ValueError("device inputs must all have the same shape (no broadcasting on the device path)")
+        if len({v[2] for v in views}) != 1:
+            raise TypeError("device inputs must share one dtype (float32 or float64)")
+        if full:
+            M, N = 1, int(np.prod(shape, dtype=np.int64))
+        else:
+            if sorted(axis) != list(_range(nd - len(axis), nd)):
+                raise NotImplementedError("device inputs support reducing the trailing axes only (or all axes)")
+            N = int(np.prod(shape[nd - len(axis):], dtype=np.int64))
+            M = int(np.prod(shape[: nd - len(axis)], dtype=np.int64))
+        dev = views[0][3]
+        out = _device_call(views, wview, bins, M, N, dev, _flags, _timing)
+        return out.reshape(kept_axes_shape + nbins)
+
+    data = [_as_float_data(np.asarray(a)) for a in all_arrays]
+    if len({a.dtype for a in data}) > 1:
+        data = [a.astype(np.float64) for a in data]   # exact: float32 -> float64 (numpy promotes the same way)
+    if w is not None:
+        w = _as_float_weights(np.asarray(w))
+    ax = None if full else list(axis)
+    rows = [_rows_view(a, ax, full) for a in data]
+    M, N = rows[0][2], rows[0][3]
+    wrow = _rows_view(w, ax, full) if w is not None else None
+    xdt = _xh_dtype(data[0].dtype)
+    out = _host_call([r[0] for r in rows], [r[1] for r in rows], wrow, bins, M, N, xdt, _devices, _flags, _timing)
+    return out.reshape(kept_axes_shape + nbins)
+
+
+def _host_call(arrs, strides, wrow, bins, M, N, xdt, devices, flags, timing):
+    d_dtype = xdt
+    w2d, wstride, wdt = (wrow[0], wrow[1], _xh_dtype(wrow[0].dtype)) if wrow is not None else (None, 0, _cabi.XH_NONE)
+    return _desc_call(arrs, strides, w2d, wstride, bins, M, N, d_dtype, wdt, _cabi.XH_HOST,
+                      devices[0] if devices else _default_device(), devices, flags, timing)
+
+
+def _device_call(views, wview, bins, M, N, dev, flags, timing):
+    ptrs = [v[0] for v in views]
+    wptr = wview[0] if wview else None
+    wdt = _xh_dtype(wview[2]) if wview else _cabi.XH_NONE
+    return _desc_call(ptrs, [N] * len(ptrs), wptr, N if wview else 0, bins, M, N, _xh_dtype(views[0][2]), wdt,
+                      _cabi.XH_DEVICE, dev, None, flags, timing)
+
+
+def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing):
+    K = len(arrs)
+    if K > _cabi.XH_MAX_VARS:
+        raise NotImplementedError(f"at most {_cabi.XH_MAX_VARS} variables are supported")
+    d = _cabi.XhDesc()
+    d.n_vars, d.dtype, d.w_dtype, d.mem, d.out_mem, d.device, d.flags = K, dtype, wdtype, mem, _cabi.XH_HOST, device, flags | _debug_flags
+    d.n_rows, d.n_cols = M, N
+    keep = []
+    for k in _range(K):
+        if mem == _cabi.XH_HOST:
+            d.data[k] = arrs[k].ctypes.data if arrs[k].size else None
+        else:
+            d.data[k] = arrs[k]
+        d.row_stride[k] = strides[k]
+        e = np.ascontiguousarray(bins[k], dtype=np.float64)
+        keep.append(e)
+        d.edges[k] = e.ctypes.data_as(C.POINTER(C.c_double))
+        d.n_edges[k] = e.size
+    if w is not None:
+        d.weights = (w.ctypes.data if w.size else None) if mem == _cabi.XH_HOST else w
+        d.w_row_stride = wstride
+        if mem == _cabi.XH_HOST and not w.size:
+            d.w_dtype = _cabi.XH_NONE
+    B = int(np.prod([len(b) - 1 for b in bins], dtype=np.int64))
+    out = np.empty((M, B), dtype=np.int64 if w is None else np.float64)
+    if M * N == 0 or B == 0:
+        out[...] = 0
+        return out
+    d.out = out.ctypes.data
+    ms = C.c_float(0.0)
+    if timing is not None:
+        d.kernel_ms = C.pointer(ms)
+    if devices is not None and len(devices) > 1:
+        arr = (C.c_int32 * len(devices))(*devices)
+        _cabi.check(_cabi.lib().xh_hist_multi(C.byref(d), arr, len(devices)), "xh_hist_multi")
+    else:
+        _cabi.check(_cabi.lib().xh_hist(C.byref(d)), "xh_hist")
+    if timing is not None:
+        timing["kernel_ms"] = ms.value
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# public entry point (reference: core.py:250-466)
+# --------------------------------------------------------------------------------------------
+def histogram(*args, bins=None, range=None, axis=None, weights=None, density=False, block_size="auto",
+              devices=None):
+    """Histogram applied along specified axis / axes — signature of ``xhistogram.core.histogram``.
+
+    Parameters are those of the reference (see its docstring, core.py:259-333).  ``devices``
+    (extension, optional): list of CUDA ordinals to shard a host-resident request over; rows
+    are split when enough rows are kept, otherwise the reduced axis is split and the partial
+    histograms are summed with NCCL.
+
+    Returns ``(hist, bin_edges)``: ``hist`` has the kept axes (original order) followed by one
+    axis per argument; int64 counts, or float64 when ``weights`` or ``density`` is given.
+    """
+    if len(args) == 0:
+        raise TypeError("histogram() needs at least one array")
+    if block_size is not None and block_size != "auto" and not isinstance(block_size, (int, np.integer)):
+        raise TypeError("block_size must be None, an int or 'auto'")
+    is_dask_array = any(_is_dask(a) for a in list(args) + [weights])
+    device_inputs = any(is_device_array(a) for a in list(args) + [weights])
+    if device_inputs and not all(is_device_array(a) for a in list(args) + ([weights] if weights is not None else [])):
+        raise TypeError("cannot mix device-resident and host arrays in one call")
+    if not is_dask_array and not device_inputs:
+        args = tuple(np.asarray(a) for a in args)
+        weights = None if weights is None else np.asarray(weights)
+
+    a0 = args[0]
+    ndim = len(as_device_view(a0)[1]) if device_inputs else a0.ndim
+    n_inputs = len(args)
+
+    if axis is not None:                                             # core.py:341-352
+        axis = np.atleast_1d(axis)
+        assert axis.ndim == 1
+        axis_normed = []
+        for ax in axis:
+            ax_positive = ax if ax >= 0 else ndim + ax
+            assert ax_positive < ndim, "axis must be less than ndim"
+            axis_normed.append(ax_positive)
+        axis = [int(i) for i in axis_normed]
+
+    all_arrays = list(args)
+    has_weights = weights is not None
+    if has_weights:
+        all_arrays.append(weights)
+
+    if device_inputs:
+        shapes = {as_device_view(a)[1] for a in all_arrays}
+        if len(shapes) != 1:
+            raise ValueError("device inputs must all have the same shape")
+        input_ndim = ndim
+    elif is_dask_array:
+        import dask.array as dsa
+        all_arrays = list(dsa.broadcast_arrays(*all_arrays))
+        input_ndim = all_arrays[0].ndim
+    else:
+        all_arrays = list(np.broadcast_arrays(*all_arrays))          # core.py:366 (views; rows of stride 0 stay un-materialised)
+        input_ndim = all_arrays[0].ndim
+    input_axes = tuple(_range(input_ndim))
+
+    bins = _ensure_correctly_formatted_bins(bins, n_inputs)
+    range = _ensure_correctly_formatted_range(range, n_inputs)
+
+    if is_dask_array:
+        if not all(isinstance(b, np.ndarray) for b in bins):
+            raise TypeError("When using dask arrays, bins must be provided as numpy array(s) of edges")
+    else:
+        w_for_edges = all_arrays[-1] if has_weights else None
+        bins = [_resolve_edges(a, b, r, w_for_edges) for a, b, r in zip(all_arrays, bins, range)]
+
+    for b in bins:
+        if np.asarray(b).dtype.kind not in "fiu":
+            raise TypeError(f"unsupported bin-edge dtype {np.asarray(b).dtype} for the B200 histogram path")
+
+    drop_axes = tuple(axis) if axis is not None else input_axes
+    bincount_kwargs = dict(weights=has_weights, axis=axis, bins=bins, density=density, block_size=block_size)
+
+    if is_dask_array:
+        import dask.array as dsa                                      # core.py:403-439, _bincount now on the GPU
+        adjust_chunks = {i: (lambda x: 1) for i in drop_axes}
+        new_axes_start = max(input_axes) + 1
+        new_axes = {new_axes_start + i: len(b) - 1 for i, b in enumerate(bins)}
+        out_index = input_axes + tuple(new_axes)
+        blockwise_args = []
+        for arg in all_arrays:
+            blockwise_args += [arg, input_axes]
+        dtype = "i8" if not has_weights else "f8"
+        bin_counts = dsa.blockwise(_bincount, out_index, *blockwise_args, new_axes=new_axes,
+                                   adjust_chunks=adjust_chunks, meta=np.array((), dtype), **bincount_kwargs)
+        bin_counts = bin_counts.sum(drop_axes)
+    else:
+        bin_counts = _bincount(*all_arrays, _devices=devices, **bincount_kwargs).squeeze(drop_axes)
+
+    if density:                                                      # core.py:444-462
+        bin_widths = [np.diff(b) for b in bins]
+        bin_areas = functools.reduce(np.multiply.outer, bin_widths)  # K=1: widths, K=2: outer, K>=3: N-D outer
+        bin_axes = tuple(_range(-n_inputs, 0))
+        bin_count_sums = bin_counts.sum(axis=bin_axes)
+        sums_shape = bin_count_sums.shape + len(bin_axes) * (1,)
+        h = bin_counts / bin_areas / np.reshape(bin_count_sums, sums_shape)
+    else:
+        h = bin_counts
+    return h, bins

@@ -1,0 +1,774 @@
+// xhist_api.cu — host side of the C-ABI declared in include/xhist_b200.h.
+//
+// Responsibilities: per-device context (stream, workspaces), exact preparation of the bin
+// edges for the device compare (SURVEY.md §8a rules R1/R2), the launch plan (shared-memory
+// histogram mode, partition, grid), the pinned/pageable host->device pipeline for host
+// inputs, the single-process multi-GPU fan-out and the NCCL reduction of partial histograms.
+// The O(samples) work itself is only ever done by the kernels in xhist_kernels.cu — there is
+// no CPU fallback: if no sm_100 device is usable every entry point fails with XH_ERR_NO_DEVICE.
+#include "../../include/xhist_b200.h"
+#include "xhist_kernels.cuh"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail(e__ == cudaErrorMemoryAllocation ? XH_ERR_NOMEM : XH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                      \
+  } while (0)
+
+size_t dsize(int dt) { return dt == XH_F32 ? 4 : dt == XH_F64 ? 8 : 0; }
+
+// ------------------------------------------------------------------------------------------ NCCL (dlopen)
+struct Id128 { char b[XH_NCCL_UNIQUE_ID_BYTES]; };
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int nccl_load() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.handle) return XH_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+  if (!h) return fail(XH_ERR_NCCL, "NCCL not found (dlopen libnccl.so.2): %s", dlerror());
+#define SYM(field, name)                                                             \
+  *reinterpret_cast<void**>(&g_nccl.field) = dlsym(h, name);                         \
+  if (!g_nccl.field) return fail(XH_ERR_NCCL, "NCCL symbol %s missing", name);
+  SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommInitAll, "ncclCommInitAll")
+  SYM(CommDestroy, "ncclCommDestroy") SYM(AllReduce, "ncclAllReduce") SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.handle = h;
+  return XH_OK;
+}
+#define NC(call)                                                                                  \
+  do {                                                                                            \
+    int r__ = (call);                                                                             \
+    if (r__ != 0) return fail(XH_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__));    \
+  } while (0)
+constexpr int kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0;
+
+// ------------------------------------------------------------------------------------------ context
+struct Ctx {
+  int device = -1;
+  std::mutex mu;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+  int sm_count = 0, smem_optin = 0, smem_per_sm = 0;
+  XhkWindow* window = nullptr;       // device
+  void* edges = nullptr;             // device edge table
+  size_t edges_cap = 0;
+  double* minmax = nullptr;          // device [296*3]
+  void* stage[2] = {nullptr, nullptr};  // device staging slots for host inputs
+  size_t stage_cap = 0;
+  void* bcast = nullptr;             // device copies of broadcast (stride 0) rows
+  size_t bcast_cap = 0;
+  void* flush = nullptr;             // L2 flush scratch
+  size_t flush_bytes = 0;
+  void* outbuf = nullptr;            // device histogram when the caller's out is host memory
+  size_t outbuf_cap = 0;
+  void* comm = nullptr;              // NCCL communicator (multi-process mode)
+};
+
+std::mutex g_ctx_mu;
+std::map<int, Ctx*> g_ctx;
+
+int get_ctx(int device, Ctx** out) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto it = g_ctx.find(device);
+  if (it != g_ctx.end()) { *out = it->second; return XH_OK; }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(XH_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(XH_ERR_INVALID, "device %d out of range (have %d)", device, n);
+  cudaDeviceProp pr;
+  CU(cudaGetDeviceProperties(&pr, device));
+  if (pr.major != 10) return fail(XH_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, pr.major, pr.minor);
+  CU(cudaSetDevice(device));
+  Ctx* c = new Ctx();
+  c->device = device; c->sm_count = pr.multiProcessorCount;
+  c->smem_optin = static_cast<int>(pr.sharedMemPerBlockOptin);
+  c->smem_per_sm = static_cast<int>(pr.sharedMemPerMultiprocessor);
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&c->ev0)); CU(cudaEventCreate(&c->ev1)); CU(cudaEventCreate(&c->tev0)); CU(cudaEventCreate(&c->tev1));
+  for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&c->copied[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->consumed[i], cudaEventDisableTiming)); }
+  CU(cudaMalloc(&c->window, sizeof(XhkWindow)));
+  CU(cudaMalloc(&c->minmax, 296 * 3 * sizeof(double)));
+  CU(xhk_set_smem_limits(c->smem_optin - 64));  // 64 B of static shared memory in k_hist
+  g_ctx[device] = c;
+  *out = c;
+  return XH_OK;
+}
+
+// ------------------------------------------------------------------------------------------ edges
+// Effective edges for the device compare.  numpy compares data and edges after promotion
+// (fp32 data vs float64 edges -> float64).  For fp32 data x and a float64 edge e:
+//   e <= x  <=>  up32(e) <= x   with up32(e) the smallest fp32 >= e,
+//   x <= e  <=>  x <= dn32(e)   with dn32(e) the largest  fp32 <= e,
+// so an fp32 compare against the rounded-up edges is exact.
+float up32(double e) { float f = static_cast<float>(e); if (static_cast<double>(f) < e) f = std::nextafterf(f, INFINITY); return f; }
+float dn32(double e) { float f = static_cast<float>(e); if (static_cast<double>(f) > e) f = std::nextafterf(f, -INFINITY); return f; }
+
+template <typename T> void put_slot(double& s, T v) { s = 0.0; std::memcpy(&s, &v, sizeof(T)); }
+
+// Fill the classification constants of variable k; append its effective edges to `table`.
+template <typename T>
+int prep_var(const double* e, int E, int k, bool force_search, XhkParams& p, std::vector<T>& table) {
+  for (int j = 0; j < E; ++j) if (std::isnan(e[j])) return fail(XH_ERR_INVALID, "edges of variable %d contain NaN", k);
+  for (int j = 1; j < E; ++j) if (e[j] < e[j - 1]) return fail(XH_ERR_INVALID, "edges of variable %d must increase monotonically", k);
+  p.nb[k] = E - 1;
+  p.eoff[k] = static_cast<int>(table.size());
+  const bool f32 = sizeof(T) == 4;
+  for (int j = 0; j < E; ++j) table.push_back(f32 ? static_cast<T>(up32(e[j])) : static_cast<T>(e[j]));
+  const T lo = table[p.eoff[k]];
+  const T hi = f32 ? static_cast<T>(dn32(e[E - 1])) : static_cast<T>(e[E - 1]);
+  put_slot<T>(p.lo[k], lo); put_slot<T>(p.hi[k], hi);
+  p.uniform[k] = 0;
+  put_slot<T>(p.e0[k], T(0)); put_slot<T>(p.inv[k], T(0)); put_slot<T>(p.delta[k], T(2)); put_slot<T>(p.omd[k], T(-1));
+  if (force_search) return XH_OK;
+  // uniform fast path: usable when the edges are an arithmetic progression up to a small, bounded deviation
+  const long double e0 = e[0], eN = e[E - 1];
+  if (!std::isfinite(static_cast<double>(e0)) || !std::isfinite(static_cast<double>(eN)) || !(eN > e0)) return XH_OK;
+  const long double w = (eN - e0) / (E - 1);
+  if (!(w > 0) || !std::isfinite(static_cast<double>(w))) return XH_OK;
+  long double dev = 0;  // max deviation of the effective edges from e0 + j*w, in bin units
+  for (int j = 0; j < E; ++j) {
+    const long double eff = static_cast<long double>(table[p.eoff[k] + j]);
+    dev = std::max(dev, std::fabs(eff - (e0 + j * w)) / w);
+  }
+  const long double u = f32 ? std::ldexp(1.0L, -24) : std::ldexp(1.0L, -53);
+  const T e0T = static_cast<T>(static_cast<double>(e0));
+  const T invT = static_cast<T>(static_cast<double>(1.0L / w));
+  if (!std::isfinite(static_cast<double>(invT)) || invT <= T(0)) return XH_OK;
+  const long double d0 = std::fabs(static_cast<long double>(e0T) - e0) / w;
+  const long double dinv = std::fabs(static_cast<long double>(invT) * w - 1.0L);  // relative error of inv
+  // |t_hat - tau| <= d0 + (E + d0) * (2u + dinv + slack)   (one rounding in the subtraction, one in the product)
+  const long double eps_t = d0 + (E + d0) * (2 * u + dinv + u) + 1e-30L;
+  const long double delta = 2 * (eps_t + dev) + 4 * u;
+  if (!(delta < 0.125L)) return XH_OK;
+  // round delta up and 1-delta down in T
+  T dT = static_cast<T>(static_cast<double>(delta)); if (static_cast<long double>(dT) < delta) dT = std::nextafter(dT, T(1));
+  T oT = static_cast<T>(static_cast<double>(1.0L - delta)); if (static_cast<long double>(oT) > 1.0L - delta) oT = std::nextafter(oT, T(0));
+  put_slot<T>(p.e0[k], e0T); put_slot<T>(p.inv[k], invT); put_slot<T>(p.delta[k], dT); put_slot<T>(p.omd[k], oT);
+  p.uniform[k] = 1;
+  return XH_OK;
+}
+
+// ------------------------------------------------------------------------------------------ plan + launch
+struct Plan {
+  XhkParams p;
+  XhkLaunch l;
+  bool need_window = false;
+  int window_budget = 0;
+  enum Zero { ZERO_NONE, ZERO_ALL, ZERO_SHARED } zero = ZERO_NONE;
+};
+
+// Per-call preparation shared by every block of the call: classification constants and the
+// effective-edge table (uploaded once), bin-space geometry.
+struct Prep {
+  XhkParams base;
+  std::vector<unsigned char> edge_host;
+  size_t edges_al = 0;
+};
+
+int prep_call(const xh_desc* d, Prep& pr) {
+  XhkParams& p = pr.base;
+  std::memset(&p, 0, sizeof p);
+  const int K = d->n_vars;
+  const size_t tsz = dsize(d->dtype);
+  p.n_vars = K;
+  const bool force_search = (d->flags & XH_FLAG_FORCE_SEARCH) != 0;
+  std::vector<float> tf; std::vector<double> td;
+  for (int k = 0; k < K; ++k) {
+    int rc = (d->dtype == XH_F32) ? prep_var<float>(d->edges[k], d->n_edges[k], k, force_search, p, tf)
+                                  : prep_var<double>(d->edges[k], d->n_edges[k], k, force_search, p, td);
+    if (rc) return rc;
+  }
+  long long B = 1;
+  for (int k = 0; k < K; ++k) {
+    if (B > (1ll << 40) / std::max(1, p.nb[k])) return fail(XH_ERR_INVALID, "bin space too large");
+    B *= p.nb[k];
+  }
+  p.B = B;
+  long long mul = 1;
+  for (int k = K - 1; k >= 0; --k) { p.gmul[k] = mul; mul *= p.nb[k]; }
+  p.n_edges_total = static_cast<int>(d->dtype == XH_F32 ? tf.size() : td.size());
+  const size_t edge_bytes = p.n_edges_total * tsz;
+  pr.edge_host.resize(edge_bytes);
+  std::memcpy(pr.edge_host.data(), d->dtype == XH_F32 ? static_cast<const void*>(tf.data()) : static_cast<const void*>(td.data()), edge_bytes);
+  pr.edges_al = (edge_bytes + 15) & ~static_cast<size_t>(15);
+  return XH_OK;
+}
+
+int upload_edges(Ctx* c, const Prep& pr, cudaStream_t s) {
+  const size_t bytes = pr.edge_host.size();
+  if (bytes > c->edges_cap) {
+    if (c->edges) cudaFree(c->edges);
+    c->edges = nullptr; c->edges_cap = 0;
+    size_t cap = std::max<size_t>(bytes, 1 << 16);
+    CU(cudaMalloc(&c->edges, cap));
+    c->edges_cap = cap;
+  }
+  CU(cudaMemcpyAsync(c->edges, pr.edge_host.data(), bytes, cudaMemcpyHostToDevice, s));
+  return XH_OK;
+}
+
+// Launch plan of one block whose data/weights/out pointers are DEVICE pointers.
+int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Plan& pl) {
+  XhkParams& p = pl.p;
+  p = pr.base;
+  const int K = d->n_vars;
+  p.M = d->n_rows; p.N = d->n_cols;
+  for (int k = 0; k < K; ++k) { p.data[k] = d->data[k]; p.stride[k] = d->row_stride[k]; }
+  p.w = d->weights; p.wstride = d->w_row_stride;
+  p.out = d->out;
+  p.window = c->window;
+  p.edges = c->edges;
+  const long long B = p.B;
+
+  // shared-memory budget
+  const size_t edges_al = pr.edges_al;
+  const size_t item = d->w_dtype == XH_NONE ? 4 : 8;
+  const long long budget1 = static_cast<long long>(c->smem_optin) - 64 - static_cast<long long>(edges_al);  // 1 CTA / SM
+  if (budget1 < 0) return fail(XH_ERR_UNSUPPORTED, "bin edges (%zu bytes) do not fit in shared memory", pr.edge_host.size());
+  const long long cap1 = budget1 / static_cast<long long>(item);
+  int mode;
+  if (d->flags & XH_FLAG_FORCE_GLOBAL) mode = XHK_GLOBAL;
+  else if (B <= cap1 && !(d->flags & XH_FLAG_FORCE_WINDOW)) mode = XHK_FULL;
+  else mode = XHK_WINDOW;
+  long long marg_bytes = 0; for (int k = 0; k < K; ++k) marg_bytes += 4ll * p.nb[k];
+  if (mode == XHK_WINDOW && (static_cast<long long>(edges_al) + marg_bytes > c->smem_optin - 256 || cap1 < 1)) mode = XHK_GLOBAL;
+  p.hist_mode = mode;
+
+  int ctas_per_sm = 1, threads = 1024;
+  size_t smem = edges_al;
+  if (mode == XHK_FULL) {
+    smem = edges_al + static_cast<size_t>(B) * item;
+    // two 512-thread CTAs per SM when both histograms fit (a flush of one overlaps the stream of the other)
+    if (2 * (smem + 1024 + 64) <= static_cast<size_t>(c->smem_per_sm)) { ctas_per_sm = 2; threads = 512; }
+    p.hist_capacity = static_cast<int>(B);
+  } else if (mode == XHK_WINDOW) {
+    long long cap = cap1;
+    if (d->flags & XH_FLAG_FORCE_WINDOW) cap = std::max<long long>(1, std::min<long long>(cap1, B / 3));
+    pl.need_window = true; pl.window_budget = static_cast<int>(std::min<long long>(cap, 1ll << 30));
+    smem = edges_al + static_cast<size_t>(pl.window_budget) * item;
+    p.hist_capacity = pl.window_budget;
+  } else {
+    ctas_per_sm = 2; threads = 512;
+  }
+  const long long total = p.M * p.N;
+  int grid = c->sm_count * ctas_per_sm;
+  const long long min_per_cta = 4096;
+  if (total < static_cast<long long>(grid) * min_per_cta) grid = static_cast<int>(std::max<long long>(1, (total + min_per_cta - 1) / min_per_cta));
+  if (p.M >= 16ll * grid) p.partition = XHK_PART_ROWS;
+  else {
+    p.partition = XHK_PART_SAMPLES;
+    long long per = (total + grid - 1) / grid;
+    per = (per + 1023) / 1024 * 1024;
+    p.per_cta = per;
+    grid = static_cast<int>((total + per - 1) / per);
+  }
+  const bool no_zero = (d->flags & XH_FLAG_NO_ZERO) != 0;
+  p.store_owned_rows = (mode == XHK_FULL && !no_zero && !(p.M > 1 && p.N > (1ll << 30))) ? 1 : 0;
+  if (no_zero) pl.zero = Plan::ZERO_NONE;
+  else if (p.store_owned_rows) pl.zero = (p.partition == XHK_PART_ROWS) ? Plan::ZERO_NONE : Plan::ZERO_SHARED;
+  else pl.zero = Plan::ZERO_ALL;
+  pl.l.dtype = d->dtype; pl.l.w_dtype = d->w_dtype; pl.l.grid = grid; pl.l.threads = threads; pl.l.smem_bytes = smem; pl.l.stream = stream;
+  return XH_OK;
+}
+
+// Enqueue zero-fill, window selection and the histogram kernel of one planned block.
+int enqueue(Ctx* c, Plan& pl) {
+  cudaStream_t s = pl.l.stream;
+  const size_t osz = 8;
+  if (pl.zero == Plan::ZERO_ALL) CU(cudaMemsetAsync(pl.p.out, 0, static_cast<size_t>(pl.p.M) * pl.p.B * osz, s));
+  else if (pl.zero == Plan::ZERO_SHARED) CU(xhk_launch_zero_shared_rows(pl.p, pl.l));
+  if (pl.need_window) {
+    const long long total = pl.p.M * pl.p.N;
+    const int n_probe = static_cast<int>(std::min<long long>(total, 1 << 16));
+    CU(xhk_launch_window(pl.p, pl.l, c->window, pl.window_budget, n_probe));
+  }
+  CU(xhk_launch_hist(pl.p, pl.l));
+  return XH_OK;
+}
+
+int validate(const xh_desc* d) {
+  if (!d) return fail(XH_ERR_INVALID, "null descriptor");
+  if (d->n_vars < 1 || d->n_vars > XH_MAX_VARS) return fail(XH_ERR_INVALID, "n_vars must be 1..%d", XH_MAX_VARS);
+  if (d->dtype != XH_F32 && d->dtype != XH_F64) return fail(XH_ERR_INVALID, "dtype must be XH_F32 or XH_F64");
+  if (d->w_dtype != XH_NONE && d->w_dtype != XH_F32 && d->w_dtype != XH_F64) return fail(XH_ERR_INVALID, "bad w_dtype");
+  if ((d->w_dtype != XH_NONE) != (d->weights != nullptr)) return fail(XH_ERR_INVALID, "weights pointer and w_dtype disagree");
+  if (d->n_rows < 0 || d->n_cols < 0) return fail(XH_ERR_INVALID, "negative shape");
+  if (!d->out) return fail(XH_ERR_INVALID, "out is null");
+  for (int k = 0; k < d->n_vars; ++k) {
+    if (!d->edges[k] || d->n_edges[k] < 2) return fail(XH_ERR_INVALID, "variable %d needs at least 2 edges", k);
+    if (d->n_rows > 0 && d->n_cols > 0 && !d->data[k]) return fail(XH_ERR_INVALID, "data[%d] is null", k);
+    if (d->row_stride[k] < 0) return fail(XH_ERR_INVALID, "negative row stride");
+    if (reinterpret_cast<uintptr_t>(d->data[k]) % dsize(d->dtype)) return fail(XH_ERR_INVALID, "data[%d] is not element-aligned", k);
+  }
+  if (d->weights && reinterpret_cast<uintptr_t>(d->weights) % dsize(d->w_dtype)) return fail(XH_ERR_INVALID, "weights not element-aligned");
+  if ((d->flags & XH_FLAG_NO_ZERO) && d->out_mem != XH_DEVICE) return fail(XH_ERR_INVALID, "XH_FLAG_NO_ZERO needs a device out");
+  return XH_OK;
+}
+
+long long bins_per_row(const xh_desc* d) { long long B = 1; for (int k = 0; k < d->n_vars; ++k) B *= (d->n_edges[k] - 1); return B; }
+
+int ensure_stage(Ctx* c, size_t bytes_per_slot) {
+  if (bytes_per_slot <= c->stage_cap) return XH_OK;
+  for (int i = 0; i < 2; ++i) { if (c->stage[i]) cudaFree(c->stage[i]); c->stage[i] = nullptr; }
+  c->stage_cap = 0;
+  for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->stage[i], bytes_per_slot));
+  c->stage_cap = bytes_per_slot;
+  return XH_OK;
+}
+
+// device-resident block: everything on `stream`
+int run_device_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream) {
+  Plan pl;
+  int rc = plan_block(c, pr, d, stream, pl);
+  if (rc) return rc;
+  return enqueue(c, pl);
+}
+
+// host inputs: double-buffered H2D pipeline feeding device blocks that accumulate into dev_out
+int run_host_pipeline(Ctx* c, const Prep& pr, const xh_desc* d, void* dev_out) {
+  const int K = d->n_vars;
+  const size_t tsz = dsize(d->dtype), wsz = dsize(d->w_dtype);
+  const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
+  const int narr = K + (wsz ? 1 : 0);
+  auto arr_ptr = [&](int a) -> const unsigned char* { return static_cast<const unsigned char*>(a < K ? d->data[a] : d->weights); };
+  auto arr_stride = [&](int a) -> long long { return a < K ? d->row_stride[a] : d->w_row_stride; };
+  auto arr_size = [&](int a) -> size_t { return a < K ? tsz : wsz; };
+  const long long chunk = 1ll << 23;  // samples per staged block (32 MiB per fp32 array)
+  // broadcast rows (stride 0, M > 1) are copied once
+  size_t bc_bytes = 0;
+  std::vector<size_t> bc_off(narr, 0);
+  for (int a = 0; a < narr; ++a) if (arr_stride(a) == 0 && M > 1) { bc_off[a] = bc_bytes; bc_bytes += (static_cast<size_t>(N) * arr_size(a) + 255) & ~static_cast<size_t>(255); }
+  const bool long_rows = (N >= chunk) || M == 1;
+  if (bc_bytes && long_rows) bc_bytes = 0;  // long rows: broadcast arrays are re-staged per column chunk
+  if (bc_bytes > c->bcast_cap) {
+    if (c->bcast) cudaFree(c->bcast);
+    c->bcast = nullptr; c->bcast_cap = 0;
+    CU(cudaMalloc(&c->bcast, bc_bytes)); c->bcast_cap = bc_bytes;
+  }
+  const long long blk_samples = long_rows ? std::min(chunk, std::max<long long>(N, 1)) : (std::max<long long>(1, chunk / N) * N);
+  size_t slot_bytes = 0;
+  std::vector<size_t> slot_off(narr, 0);
+  for (int a = 0; a < narr; ++a) { slot_off[a] = slot_bytes; slot_bytes += (static_cast<size_t>(blk_samples) * arr_size(a) + 255) & ~static_cast<size_t>(255); }
+  int rc = ensure_stage(c, slot_bytes);
+  if (rc) return rc;
+  if (long_rows) CU(cudaMemsetAsync(dev_out, 0, static_cast<size_t>(M) * B * 8, c->stream));  // column chunks accumulate
+  if (bc_bytes) {
+    for (int a = 0; a < narr; ++a)
+      if (arr_stride(a) == 0 && M > 1)
+        CU(cudaMemcpyAsync(static_cast<unsigned char*>(c->bcast) + bc_off[a], arr_ptr(a), static_cast<size_t>(N) * arr_size(a), cudaMemcpyHostToDevice, c->stream));
+  }
+  int it = 0;
+  auto submit = [&](long long r0, long long nrows, long long c0, long long ncols) -> int {
+    const int slot = it & 1; ++it;
+    unsigned char* base = static_cast<unsigned char*>(c->stage[slot]);
+    CU(cudaStreamWaitEvent(c->copy_stream, c->consumed[slot], 0));
+    xh_desc b = *d;
+    b.mem = XH_DEVICE; b.out_mem = XH_DEVICE; b.kernel_ms = nullptr;
+    if (long_rows) b.flags |= XH_FLAG_NO_ZERO;  // whole-row blocks own their slice of out and zero/store it themselves
+    b.n_rows = nrows; b.n_cols = ncols;
+    b.out = static_cast<unsigned char*>(dev_out) + static_cast<size_t>(r0) * B * 8;
+    for (int a = 0; a < narr; ++a) {
+      const size_t es = arr_size(a);
+      const long long st = arr_stride(a);
+      const void* dev_ptr; long long dev_stride;
+      if (st == 0 && M > 1 && bc_bytes) {
+        dev_ptr = static_cast<unsigned char*>(c->bcast) + bc_off[a] + static_cast<size_t>(c0) * es; dev_stride = 0;
+      } else {
+        unsigned char* dst = base + slot_off[a];
+        const unsigned char* src = arr_ptr(a) + (static_cast<size_t>(r0) * st + c0) * es;
+        if (st == 0) { CU(cudaMemcpyAsync(dst, src, static_cast<size_t>(ncols) * es, cudaMemcpyHostToDevice, c->copy_stream)); dev_stride = 0; }
+        else if (nrows == 1 || st == ncols) { CU(cudaMemcpyAsync(dst, src, static_cast<size_t>(nrows) * ncols * es, cudaMemcpyHostToDevice, c->copy_stream)); dev_stride = ncols; }
+        else { CU(cudaMemcpy2DAsync(dst, static_cast<size_t>(ncols) * es, src, static_cast<size_t>(st) * es, static_cast<size_t>(ncols) * es, nrows, cudaMemcpyHostToDevice, c->copy_stream)); dev_stride = ncols; }
+        dev_ptr = dst;
+      }
+      if (a < K) { b.data[a] = dev_ptr; b.row_stride[a] = dev_stride; } else { b.weights = dev_ptr; b.w_row_stride = dev_stride; }
+    }
+    CU(cudaEventRecord(c->copied[slot], c->copy_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->copied[slot], 0));
+    int rc2 = run_device_block(c, pr, &b, c->stream);
+    if (rc2) return rc2;
+    CU(cudaEventRecord(c->consumed[slot], c->stream));
+    return XH_OK;
+  };
+  if (long_rows) {
+    for (long long r = 0; r < M; ++r)
+      for (long long c0 = 0; c0 < N; c0 += blk_samples) { rc = submit(r, 1, c0, std::min(blk_samples, N - c0)); if (rc) return rc; }
+  } else {
+    const long long rows_per = blk_samples / N;
+    for (long long r0 = 0; r0 < M; r0 += rows_per) { rc = submit(r0, std::min(rows_per, M - r0), 0, N); if (rc) return rc; }
+  }
+  return XH_OK;
+}
+
+int hist_locked(Ctx* c, const xh_desc* d) {
+  CU(cudaSetDevice(c->device));
+  const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
+  const size_t out_bytes = static_cast<size_t>(M) * B * 8;
+  void* dev_out = d->out;
+  if (d->out_mem == XH_HOST && out_bytes) {
+    if (out_bytes > c->outbuf_cap) {
+      if (c->outbuf) cudaFree(c->outbuf);
+      c->outbuf = nullptr; c->outbuf_cap = 0;
+      CU(cudaMalloc(&c->outbuf, out_bytes));
+      c->outbuf_cap = out_bytes;
+    }
+    dev_out = c->outbuf;
+  }
+  Prep pr;
+  int rc = prep_call(d, pr);
+  if (rc) return rc;
+  cudaStream_t s = (d->mem == XH_DEVICE && d->stream) ? static_cast<cudaStream_t>(d->stream) : c->stream;
+  if (d->kernel_ms) cudaEventRecord(c->ev0, s);
+  if (M == 0 || N == 0 || out_bytes == 0) {
+    if (out_bytes && !(d->flags & XH_FLAG_NO_ZERO)) { cudaError_t e = cudaMemsetAsync(dev_out, 0, out_bytes, s); if (e != cudaSuccess) rc = fail(XH_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); }
+  } else {
+    rc = upload_edges(c, pr, s);
+    if (rc == XH_OK) {
+      if (d->mem == XH_DEVICE) {
+        xh_desc b = *d; b.out = dev_out; b.out_mem = XH_DEVICE;
+        rc = run_device_block(c, pr, &b, s);
+      } else {
+        rc = run_host_pipeline(c, pr, d, dev_out);
+      }
+    }
+  }
+  if (rc == XH_OK && d->kernel_ms) cudaEventRecord(c->ev1, s);
+  if (rc == XH_OK && d->out_mem == XH_HOST && out_bytes) {
+    cudaError_t e = cudaMemcpyAsync(d->out, dev_out, out_bytes, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) rc = fail(XH_ERR_CUDA, "D2H of the histogram failed: %s", cudaGetErrorString(e));
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (rc == XH_OK && e != cudaSuccess) rc = fail(XH_ERR_CUDA, "histogram kernel failed: %s", cudaGetErrorString(e));
+  if (d->mem == XH_HOST) { e = cudaStreamSynchronize(c->copy_stream); if (rc == XH_OK && e != cudaSuccess) rc = fail(XH_ERR_CUDA, "copy stream: %s", cudaGetErrorString(e)); }
+  if (rc == XH_OK && d->kernel_ms) { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); *d->kernel_ms = ms; }
+  return rc;
+}
+
+}  // namespace
+
+// ============================================================================================ C-ABI
+extern "C" {
+
+int xh_version(void) { return XH_VERSION_MAJOR * 1000 + XH_VERSION_MINOR; }
+
+int xh_last_error(char* buf, size_t len) {
+  if (!buf || !len) return XH_ERR_INVALID;
+  std::snprintf(buf, len, "%s", g_err.c_str());
+  return XH_OK;
+}
+
+int xh_device_count(int* count) {
+  if (!count) return fail(XH_ERR_INVALID, "null");
+  int n = 0; cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count = 0; return fail(XH_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+  *count = n; return XH_OK;
+}
+
+int xh_init(int device) { Ctx* c; return get_ctx(device, &c); }
+
+int xh_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  for (auto& kv : g_ctx) {
+    Ctx* c = kv.second;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->window) cudaFree(c->window);
+    if (c->edges) cudaFree(c->edges);
+    if (c->minmax) cudaFree(c->minmax);
+    for (int i = 0; i < 2; ++i) if (c->stage[i]) cudaFree(c->stage[i]);
+    if (c->bcast) cudaFree(c->bcast);
+    if (c->flush) cudaFree(c->flush);
+    if (c->outbuf) cudaFree(c->outbuf);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->copied[i]); cudaEventDestroy(c->consumed[i]); }
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->tev0); cudaEventDestroy(c->tev1);
+    cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
+    delete c;
+  }
+  g_ctx.clear();
+  return XH_OK;
+}
+
+int xh_device_info(int device, int* sm_count, int* smem_optin_bytes, int64_t* total_mem, int* cc_major, int* cc_minor) {
+  int n = 0; cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(XH_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  cudaDeviceProp pr; CU(cudaGetDeviceProperties(&pr, device));
+  if (sm_count) *sm_count = pr.multiProcessorCount;
+  if (smem_optin_bytes) *smem_optin_bytes = static_cast<int>(pr.sharedMemPerBlockOptin);
+  if (total_mem) *total_mem = static_cast<int64_t>(pr.totalGlobalMem);
+  if (cc_major) *cc_major = pr.major;
+  if (cc_minor) *cc_minor = pr.minor;
+  return XH_OK;
+}
+
+int xh_hist(const xh_desc* d) {
+  int rc = validate(d);
+  if (rc) return rc;
+  Ctx* c; rc = get_ctx(d->device, &c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  return hist_locked(c, d);
+}
+
+int xh_hist_multi(const xh_desc* d, const int32_t* devices, int32_t n_dev) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (!devices || n_dev < 1) return fail(XH_ERR_INVALID, "need at least one device");
+  if (d->mem != XH_HOST || d->out_mem != XH_HOST) return fail(XH_ERR_INVALID, "xh_hist_multi takes host data and a host out");
+  if (n_dev == 1) { xh_desc b = *d; b.device = devices[0]; return xh_hist(&b); }
+  const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
+  const size_t tsz = dsize(d->dtype), wsz = dsize(d->w_dtype);
+  std::vector<Ctx*> ctx(n_dev);
+  for (int i = 0; i < n_dev; ++i) { rc = get_ctx(devices[i], &ctx[i]); if (rc) return rc; }
+  const bool by_rows = M >= n_dev;
+  std::vector<int> rcs(n_dev, XH_OK);
+  std::vector<std::string> errs(n_dev);
+  std::vector<void*> partial(n_dev, nullptr);
+  std::vector<float> times(n_dev, 0.f);
+  if (!by_rows) { rc = nccl_load(); if (rc) return rc; }
+  // per-device shard, run concurrently (one host thread per GPU; each has its own PCIe link)
+  std::vector<std::thread> th;
+  for (int i = 0; i < n_dev; ++i) {
+    th.emplace_back([&, i]() {
+      Ctx* c = ctx[i];
+      std::lock_guard<std::mutex> lk(c->mu);
+      xh_desc b = *d;
+      b.device = devices[i]; b.kernel_ms = d->kernel_ms ? &times[i] : nullptr;
+      if (by_rows) {
+        const long long r0 = M * i / n_dev, r1 = M * (i + 1) / n_dev;
+        b.n_rows = r1 - r0;
+        for (int k = 0; k < d->n_vars; ++k) b.data[k] = static_cast<const unsigned char*>(d->data[k]) + static_cast<size_t>(r0) * d->row_stride[k] * tsz;
+        if (d->weights) b.weights = static_cast<const unsigned char*>(d->weights) + static_cast<size_t>(r0) * d->w_row_stride * wsz;
+        b.out = static_cast<unsigned char*>(d->out) + static_cast<size_t>(r0) * B * 8;  // disjoint host slices: no reduction
+        rcs[i] = b.n_rows ? hist_locked(c, &b) : XH_OK;
+      } else {
+        const long long c0 = N * i / n_dev, c1 = N * (i + 1) / n_dev;
+        b.n_cols = c1 - c0;
+        for (int k = 0; k < d->n_vars; ++k) b.data[k] = static_cast<const unsigned char*>(d->data[k]) + static_cast<size_t>(c0) * tsz;
+        if (d->weights) b.weights = static_cast<const unsigned char*>(d->weights) + static_cast<size_t>(c0) * wsz;
+        cudaSetDevice(c->device);
+        if (cudaMalloc(&partial[i], static_cast<size_t>(M) * B * 8) != cudaSuccess) { rcs[i] = XH_ERR_NOMEM; errs[i] = "partial histogram allocation failed"; return; }
+        b.out = partial[i]; b.out_mem = XH_DEVICE;
+        rcs[i] = hist_locked(c, &b);
+      }
+      if (rcs[i]) errs[i] = g_err;
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n_dev; ++i) if (rcs[i]) { for (void* q : partial) if (q) cudaFree(q); return fail(rcs[i], "device %d: %s", devices[i], errs[i].c_str()); }
+  if (d->kernel_ms) *d->kernel_ms = *std::max_element(times.begin(), times.end());
+  if (by_rows) return XH_OK;
+  // columns were sharded: sum the partial histograms with one grouped ncclAllReduce over NVLink
+  static std::mutex comm_mu;
+  static std::map<std::vector<int>, std::vector<void*>> comm_cache;
+  std::lock_guard<std::mutex> lk(comm_mu);
+  std::vector<int> key(devices, devices + n_dev);
+  auto it = comm_cache.find(key);
+  if (it == comm_cache.end()) {
+    std::vector<void*> comms(n_dev, nullptr);
+    NC(g_nccl.CommInitAll(comms.data(), n_dev, key.data()));
+    it = comm_cache.emplace(key, comms).first;
+  }
+  const size_t count = static_cast<size_t>(M) * B;
+  const int ty = d->w_dtype == XH_NONE ? kNcclInt64 : kNcclFloat64;
+  NC(g_nccl.GroupStart());
+  for (int i = 0; i < n_dev; ++i) {
+    int r = g_nccl.AllReduce(partial[i], partial[i], count, ty, kNcclSum, it->second[i], ctx[i]->stream);
+    if (r != 0) { g_nccl.GroupEnd(); return fail(XH_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r)); }
+  }
+  NC(g_nccl.GroupEnd());
+  CU(cudaSetDevice(ctx[0]->device));
+  CU(cudaMemcpyAsync(d->out, partial[0], count * 8, cudaMemcpyDeviceToHost, ctx[0]->stream));
+  for (int i = 0; i < n_dev; ++i) { CU(cudaSetDevice(ctx[i]->device)); CU(cudaStreamSynchronize(ctx[i]->stream)); }
+  for (int i = 0; i < n_dev; ++i) { cudaSetDevice(ctx[i]->device); cudaFree(partial[i]); }
+  return XH_OK;
+}
+
+int xh_minmax(int device, const void* data, int dtype, int mem, int64_t n, double* mn, double* mx) {
+  if (!mn || !mx || (dtype != XH_F32 && dtype != XH_F64) || n < 0) return fail(XH_ERR_INVALID, "bad arguments");
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  if (n == 0) return fail(XH_ERR_INVALID, "zero-size array has no min/max");
+  const size_t es = dsize(dtype);
+  double hmn = INFINITY, hmx = -INFINITY; bool nan = false;
+  std::vector<double> part(296 * 3);
+  auto reduce_dev = [&](const void* dptr, long long cnt) -> int {
+    CU(xhk_launch_minmax(dptr, dtype, cnt, c->minmax, c->stream));
+    CU(cudaMemcpyAsync(part.data(), c->minmax, part.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 296; ++i) { hmn = std::min(hmn, part[3 * i]); hmx = std::max(hmx, part[3 * i + 1]); nan = nan || part[3 * i + 2] != 0.0; }
+    return XH_OK;
+  };
+  if (mem == XH_DEVICE) { rc = reduce_dev(data, n); if (rc) return rc; }
+  else {
+    const long long chunk = 1ll << 24;
+    rc = ensure_stage(c, static_cast<size_t>(chunk) * 8); if (rc) return rc;
+    for (long long o = 0; o < n; o += chunk) {
+      const long long cnt = std::min<long long>(chunk, n - o);
+      CU(cudaMemcpyAsync(c->stage[0], static_cast<const unsigned char*>(data) + o * es, cnt * es, cudaMemcpyHostToDevice, c->stream));
+      rc = reduce_dev(c->stage[0], cnt); if (rc) return rc;
+    }
+  }
+  if (nan) { *mn = NAN; *mx = NAN; } else { *mn = hmn; *mx = hmx; }
+  return XH_OK;
+}
+
+int xh_malloc(int device, size_t bytes, void** ptr) {
+  if (!ptr) return fail(XH_ERR_INVALID, "null");
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMalloc(ptr, bytes ? bytes : 1));
+  return XH_OK;
+}
+int xh_free(int device, void* ptr) {
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  CU(cudaFree(ptr));
+  return XH_OK;
+}
+int xh_host_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return fail(XH_ERR_INVALID, "null");
+  CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+  return XH_OK;
+}
+int xh_host_free(void* ptr) { CU(cudaFreeHost(ptr)); return XH_OK; }
+
+int xh_memcpy(int device, void* dst, const void* src, size_t bytes, int dst_mem, int src_mem) {
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  cudaMemcpyKind kind = dst_mem == XH_DEVICE ? (src_mem == XH_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
+                                             : (src_mem == XH_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+  CU(cudaMemcpyAsync(dst, src, bytes, kind, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return XH_OK;
+}
+int xh_memset(int device, void* dst, int value, size_t bytes) {
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemsetAsync(dst, value, bytes, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return XH_OK;
+}
+int xh_sync(int device) {
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  CU(cudaDeviceSynchronize());
+  return XH_OK;
+}
+
+static int fill_impl(int device, void* ptr, int dtype, int64_t n, uint64_t seed, int64_t offset, int normal) {
+  if (!ptr || (dtype != XH_F32 && dtype != XH_F64) || n < 0) return fail(XH_ERR_INVALID, "bad arguments");
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  CU(xhk_launch_fill(ptr, dtype, n, seed, offset, normal, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return XH_OK;
+}
+int xh_fill_normal(int device, void* ptr, int dtype, int64_t n, uint64_t seed, int64_t offset) { return fill_impl(device, ptr, dtype, n, seed, offset, 1); }
+int xh_fill_uniform(int device, void* ptr, int dtype, int64_t n, uint64_t seed, int64_t offset) { return fill_impl(device, ptr, dtype, n, seed, offset, 0); }
+
+int xh_timer_start(int device) {
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->tev0, c->stream));
+  return XH_OK;
+}
+int xh_timer_stop(int device, float* ms) {
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->tev1, c->stream));
+  CU(cudaEventSynchronize(c->tev1));
+  float t = 0; CU(cudaEventElapsedTime(&t, c->tev0, c->tev1));
+  if (ms) *ms = t;
+  return XH_OK;
+}
+int xh_flush_l2(int device) {
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  if (!c->flush) { c->flush_bytes = static_cast<size_t>(256) << 20; CU(cudaMalloc(&c->flush, c->flush_bytes)); }
+  CU(xhk_launch_flush(c->flush, c->flush_bytes, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return XH_OK;
+}
+
+int xh_comm_unique_id(void* id128) {
+  if (!id128) return fail(XH_ERR_INVALID, "null");
+  int rc = nccl_load(); if (rc) return rc;
+  NC(g_nccl.GetUniqueId(id128));
+  return XH_OK;
+}
+int xh_comm_init_rank(int device, const void* id128, int n_ranks, int rank) {
+  if (!id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(XH_ERR_INVALID, "bad arguments");
+  int rc = nccl_load(); if (rc) return rc;
+  Ctx* c; rc = get_ctx(device, &c); if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+  Id128 id; std::memcpy(id.b, id128, sizeof id.b);
+  NC(g_nccl.CommInitRank(&c->comm, n_ranks, id, rank));
+  return XH_OK;
+}
+int xh_comm_allreduce(int device, void* dev_buf, int64_t count, int dtype_is_f64) {
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->comm) return fail(XH_ERR_NCCL, "no communicator: call xh_comm_init_rank first");
+  CU(cudaSetDevice(c->device));
+  NC(g_nccl.AllReduce(dev_buf, dev_buf, static_cast<size_t>(count), dtype_is_f64 ? kNcclFloat64 : kNcclInt64, kNcclSum, c->comm, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return XH_OK;
+}
+int xh_comm_destroy(int device) {
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (c->comm) { CU(cudaSetDevice(c->device)); NC(g_nccl.CommDestroy(c->comm)); c->comm = nullptr; }
+  return XH_OK;
+}
+
+}  // extern "C"

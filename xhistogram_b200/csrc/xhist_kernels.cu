@@ -1,0 +1,521 @@
+// xhist_kernels.cu — hand-written sm_100a kernels of the histogram hot path.
+//
+// What the reference does per block (xhistogram/core.py:137-194, 73-83): per variable a
+// searchsorted + right-edge fix (core.py:163-174), a ravel_multi_index (core.py:178-181), a
+// row-offset np.bincount (core.py:80-81) and a slice that drops the under/overflow cells
+// (core.py:191-192) — 5 numpy passes and 4 full-size temporaries per variable.  Here it is ONE
+// persistent kernel: coalesced 16-byte streaming loads of the samples, per-sample classification
+// against the edges staged in shared memory, accumulation into a privatised per-CTA
+// shared-memory histogram, and a flush to global memory (plain stores for rows a CTA owns,
+// RED atomics otherwise).  No tensor cores: this is a scatter/reduce, HBM-read bound.
+//
+// Design numbers (profiles/r1_microbench_mechanisms.log, B200): streaming 12 B/sample reaches
+// ~7.0 TB/s; shared u32 atomics are free next to the stream (~590 Gsamples/s); shared f64 CAS adds
+// reach ~340 Gsamples/s; global RED only 88 Gsamples/s — hence everything that can be privatised is.
+#include "xhist_kernels.cuh"
+#include <type_traits>
+
+namespace {
+
+constexpr int kMaxThreads = 1024;
+constexpr long long kSegCap = 1ll << 30;  // u32 shared counters are flushed at least this often
+
+template <typename T>
+__device__ __forceinline__ T slot(const double& d) { return *reinterpret_cast<const T*>(&d); }
+
+__device__ __forceinline__ int floor_to_int(float t) { return __float2int_rd(t); }
+__device__ __forceinline__ int floor_to_int(double t) { return __double2int_rd(t); }
+
+// ---------------------------------------------------------------------------------------------
+// classification: bin of x for variable k, or -1 when x is dropped.
+// Rule R1 of SURVEY.md §8a == core.py:157-174: in range iff e[0] <= x <= e[E-1]; bin =
+// #{j: e[j] <= x} - 1 with x == e[E-1] falling in the last bin.  `e` holds the EFFECTIVE edges:
+// for fp32 data each float64 edge is replaced by the smallest fp32 >= edge, which makes an fp32
+// compare decide exactly like numpy's promoted float64 compare (rule R2).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ int search_bin(const T* __restrict__ e, int nb, T x) {
+  int lo = 0, hi = nb + 1;  // #{e[j] <= x} is in [lo, hi]
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (e[mid] <= x) lo = mid + 1; else hi = mid;
+  }
+  int b = lo - 1;
+  return b > nb - 1 ? nb - 1 : b;  // right-inclusive last bin (core.py:171-173)
+}
+
+template <typename T>
+__device__ __forceinline__ int classify(const XhkParams& p, int k, const T* __restrict__ sedges, T x) {
+  const T lo = slot<T>(p.lo[k]), hi = slot<T>(p.hi[k]);
+  if (!(x >= lo && x <= hi)) return -1;  // NaN compares false: dropped (rule R3)
+  const int nb = p.nb[k];
+  if (p.uniform[k]) {
+    // Evenly spaced edges: t = (x - e0) * inv is within delta/2 of the exact position in bin units
+    // (bound computed on the host from the rounding errors and the edges' deviation from the
+    // arithmetic progression), so floor(t) is the exact bin unless frac(t) is within delta of an
+    // integer; only those samples (~1e-4 of them) pay for the search.
+    const T t = (x - slot<T>(p.e0[k])) * slot<T>(p.inv[k]);
+    const int j = floor_to_int(t);
+    const T f = t - (T)j;
+    if (f >= slot<T>(p.delta[k]) && f <= slot<T>(p.omd[k]) && j >= 0 && j < nb) return j;
+  }
+  return search_bin<T>(sedges + p.eoff[k], nb, x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// streaming loads (one-touch data: evict-first)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load4(const float* p, long long g, float (&v)[4]) {
+  float4 q = __ldcs(reinterpret_cast<const float4*>(p) + g);
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+__device__ __forceinline__ void load4(const double* p, long long g, double (&v)[4]) {
+  double2 a = __ldcs(reinterpret_cast<const double2*>(p) + 2 * g);
+  double2 b = __ldcs(reinterpret_cast<const double2*>(p) + 2 * g + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template <int W> struct WType { using type = float; };
+template <> struct WType<2> { using type = double; };
+
+// ---------------------------------------------------------------------------------------------
+// the histogram kernel
+//   T  : data type (float / double)          W : 0 no weights, 1 fp32 weights, 2 fp64 weights
+//   KT : number of variables at compile time (1..4), or 0 = runtime p.n_vars (scalar loads only)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int W, int KT>
+__global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__ XhkParams p) {
+  using HT = typename std::conditional<W == 0, unsigned int, double>::type;          // shared accumulator
+  using OT = typename std::conditional<W == 0, unsigned long long, double>::type;    // global accumulator
+  using WT = typename WType<W>::type;
+  constexpr int KMAX = KT ? KT : XHK_MAX_VARS;
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_wlo[XHK_MAX_VARS], s_wlen[XHK_MAX_VARS];
+
+  const int K = KT ? KT : p.n_vars;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  T* sedges = reinterpret_cast<T*>(smem);
+  HT* shist = reinterpret_cast<HT*>(smem + ((static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15)));
+
+  for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
+  if (tid < XHK_MAX_VARS) {
+    int lo = 0, len = 0;
+    if (tid < K) {
+      if (p.hist_mode == XHK_WINDOW) { lo = p.window->lo[tid]; len = p.window->len[tid]; }
+      else if (p.hist_mode == XHK_FULL) { lo = 0; len = p.nb[tid]; }
+    }
+    s_wlo[tid] = lo; s_wlen[tid] = len;
+  }
+  __syncthreads();
+  int wlo[KMAX], wlen[KMAX];
+  int wtot = (p.hist_mode == XHK_GLOBAL) ? 0 : 1;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < K) { wlo[k] = s_wlo[k]; wlen[k] = s_wlen[k]; wtot *= wlen[k]; } else { wlo[k] = 0; wlen[k] = 0; }
+  }
+  for (int i = tid; i < wtot; i += nthr) shist[i] = HT(0);
+  __syncthreads();
+
+  OT* const out = static_cast<OT*>(p.out);
+  const long long total = p.M * p.N;
+  long long s0, s1;
+  if (p.partition == XHK_PART_ROWS) {
+    s0 = (p.M * blockIdx.x / gridDim.x) * p.N;
+    s1 = (p.M * (blockIdx.x + 1ll) / gridDim.x) * p.N;
+  } else {
+    s0 = blockIdx.x * p.per_cta; if (s0 > total) s0 = total;
+    s1 = s0 + p.per_cta; if (s1 > total) s1 = total;
+  }
+
+  // one sample: classify every variable, then add to the shared window or spill to global
+  auto sample = [&](const T (&x)[KMAX], double wv, OT* out_row) {
+    int j[KMAX]; int wbin = 0; bool ok = true, inwin = true;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        j[k] = classify<T>(p, k, sedges, x[k]);
+        ok = ok && (j[k] >= 0);
+        const unsigned jw = static_cast<unsigned>(j[k] - wlo[k]);
+        inwin = inwin && (jw < static_cast<unsigned>(wlen[k]));  // also false for j == -1
+        wbin = wbin * wlen[k] + static_cast<int>(jw);
+      }
+    }
+    if (inwin) {
+      if constexpr (W == 0) atomicAdd(reinterpret_cast<unsigned int*>(shist) + wbin, 1u);
+      else atomicAdd(reinterpret_cast<double*>(shist) + wbin, wv);
+    } else if (ok) {
+      long long gbin = 0;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) if (k < K) gbin = gbin * p.nb[k] + j[k];
+      if constexpr (W == 0) atomicAdd(reinterpret_cast<unsigned long long*>(out_row) + gbin, 1ull);
+      else atomicAdd(reinterpret_cast<double*>(out_row) + gbin, wv);
+    }
+  };
+
+  long long s = s0;
+  while (s < s1) {
+    const long long r = s / p.N;
+    const long long c0 = s - r * p.N;
+    long long len = p.N - c0;
+    if (len > s1 - s) len = s1 - s;
+    if (len > kSegCap) len = kSegCap;
+    OT* out_row = out + r * p.B;
+
+    const T* px[KMAX];
+    bool vec_ok = (KT != 0);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      px[k] = (k < K) ? static_cast<const T*>(p.data[k]) + r * p.stride[k] + c0 : nullptr;
+    const WT* pw = (W != 0) ? static_cast<const WT*>(p.w) + r * p.wstride + c0 : nullptr;
+    long long head = ((16 - (reinterpret_cast<uintptr_t>(px[0]) & 15)) & 15) / sizeof(T);
+    if (head > len) head = len;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(px[k] + head) & 15) == 0);
+    if (W != 0) vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(pw + head) & 15) == 0);
+    if (!vec_ok) head = len;
+    const long long nvec = (len - head) >> 2;  // groups of 4 samples
+    const long long tail0 = head + (nvec << 2);
+
+    // scalar head and tail (and everything when the arrays are not mutually 16-byte alignable)
+    auto scalar_at = [&](long long i) {
+      T x[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) x[k] = (k < K) ? px[k][i] : T(0);
+      double wv = 1.0;
+      if (W != 0) wv = static_cast<double>(pw[i]);
+      sample(x, wv, out_row);
+    };
+    for (long long i = tid; i < head; i += nthr) scalar_at(i);
+    for (long long i = tail0 + tid; i < len; i += nthr) scalar_at(i);
+
+    if constexpr (KT != 0) {
+      // vector body: 4 samples per thread per step, two steps in flight for small records
+      constexpr int U = (sizeof(T) * KMAX + (W == 0 ? 0 : sizeof(WT)) <= 12) ? 2 : 1;
+      for (long long g = tid; g < nvec; g += static_cast<long long>(U) * nthr) {
+        T xv[U][KMAX][4];
+        WT wv[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long gu = g + static_cast<long long>(u) * nthr;
+          if (gu < nvec) {
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) load4(px[k] + head, gu, xv[u][k]);
+            if (W != 0) load4(pw + head, gu, wv[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long gu = g + static_cast<long long>(u) * nthr;
+          if (gu < nvec) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              T x[KMAX];
+#pragma unroll
+              for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
+              sample(x, (W != 0) ? static_cast<double>(wv[u][e]) : 1.0, out_row);
+            }
+          }
+        }
+      }
+    }
+    s += len;
+
+    // ---- flush the shared histogram of this row segment and clear it
+    __syncthreads();
+    if (p.hist_mode == XHK_FULL) {
+      const bool owned = p.store_owned_rows && c0 == 0 && len == p.N;
+      if (owned) {
+        for (int b = tid; b < wtot; b += nthr) { out_row[b] = static_cast<OT>(shist[b]); shist[b] = HT(0); }
+      } else {
+        for (int b = tid; b < wtot; b += nthr) {
+          const HT v = shist[b];
+          if (v != HT(0)) { atomicAdd(out_row + b, static_cast<OT>(v)); shist[b] = HT(0); }
+        }
+      }
+    } else if (p.hist_mode == XHK_WINDOW) {
+      for (int b = tid; b < wtot; b += nthr) {
+        const HT v = shist[b];
+        if (v != HT(0)) {
+          int rem = b; long long gbin = 0;
+#pragma unroll
+          for (int k = KMAX - 1; k >= 0; --k) {
+            if (k < K) { const int q = rem / wlen[k]; const int c = rem - q * wlen[k]; rem = q; gbin += (wlo[k] + c) * p.gmul[k]; }
+          }
+          atomicAdd(out_row + gbin, static_cast<OT>(v));
+          shist[b] = HT(0);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// window selection (XHK_WINDOW): marginal histograms of a strided probe of the block, then the
+// densest hyper-rectangle of at most `budget` bins (threshold search + greedy growth).
+// One CTA; its cost (~tens of microseconds) is paid only when the bin space exceeds shared memory.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant__ XhkParams p, XhkWindow* wout, int budget,
+                                                           int n_probe) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_first[XHK_MAX_VARS], s_last[XHK_MAX_VARS], s_moff[XHK_MAX_VARS + 1];
+  __shared__ unsigned long long s_lo, s_hi;
+  __shared__ int s_fits;
+  const int K = p.n_vars, tid = threadIdx.x, nthr = blockDim.x;
+  T* sedges = reinterpret_cast<T*>(smem);
+  unsigned int* marg = reinterpret_cast<unsigned int*>(smem + ((static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15)));
+  for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
+  if (tid == 0) { int o = 0; for (int k = 0; k < K; ++k) { s_moff[k] = o; o += p.nb[k]; } s_moff[K] = o; }
+  __syncthreads();
+  const int mtot = s_moff[K];
+  for (int i = tid; i < mtot; i += nthr) marg[i] = 0u;
+  __syncthreads();
+  const long long total = p.M * p.N;
+  const long long step = total / n_probe > 0 ? total / n_probe : 1;
+  for (long long i = tid; i < n_probe; i += nthr) {
+    const long long pos = i * step;
+    if (pos >= total) break;
+    const long long r = pos / p.N, c = pos - r * p.N;
+    int j[XHK_MAX_VARS]; bool ok = true;
+    for (int k = 0; k < K; ++k) {
+      const T x = (static_cast<const T*>(p.data[k]) + r * p.stride[k])[c];
+      j[k] = classify<T>(p, k, sedges, x);
+      ok = ok && j[k] >= 0;
+    }
+    if (ok) for (int k = 0; k < K; ++k) atomicAdd(&marg[s_moff[k] + j[k]], 1u);
+  }
+  __syncthreads();
+  // density of slice s of variable k: marg * nb[k]  (equal for all slices of a uniform distribution)
+  auto volume_at = [&](unsigned long long th) -> long long {
+    if (tid < XHK_MAX_VARS) { s_first[tid] = 0x7fffffff; s_last[tid] = -1; }
+    __syncthreads();
+    for (int k = 0; k < K; ++k)
+      for (int s = tid; s < p.nb[k]; s += nthr)
+        if (static_cast<unsigned long long>(marg[s_moff[k] + s]) * p.nb[k] >= th) { atomicMin(&s_first[k], s); atomicMax(&s_last[k], s); }
+    __syncthreads();
+    long long vol = 1;
+    for (int k = 0; k < K; ++k) { int l = s_last[k] - s_first[k] + 1; if (s_last[k] < 0) l = 1; vol *= l; if (vol > (1ll << 40)) vol = 1ll << 40; }
+    __syncthreads();
+    return vol;
+  };
+  if (tid == 0) {
+    unsigned long long mx = 0;
+    for (int k = 0; k < K; ++k) for (int s = 0; s < p.nb[k]; ++s) { unsigned long long d = static_cast<unsigned long long>(marg[s_moff[k] + s]) * p.nb[k]; if (d > mx) mx = d; }
+    s_lo = 0; s_hi = mx + 1;
+  }
+  __syncthreads();
+  {
+    const long long v0 = volume_at(1);  // every slice that saw at least one probe sample
+    if (tid == 0) s_fits = (v0 <= budget);
+    __syncthreads();
+  }
+  if (!s_fits) {
+    while (true) {
+      const unsigned long long lo = s_lo, hi = s_hi;
+      if (hi - lo <= 1) break;
+      const unsigned long long mid = lo + (hi - lo) / 2;
+      const long long v = volume_at(mid);
+      if (tid == 0) { if (v <= budget) s_hi = mid; else s_lo = mid; }
+      __syncthreads();
+    }
+  }
+  // the box of the final threshold is recomputed serially (sum of nb entries: trivial)
+  if (tid == 0) {
+    const unsigned long long th = s_fits ? 1ull : s_hi;
+    int lo[XHK_MAX_VARS], len[XHK_MAX_VARS];
+    long long vol = 1;
+    for (int k = 0; k < K; ++k) {
+      int first = -1, last = -1, arg = 0; unsigned int best = 0;
+      for (int s = 0; s < p.nb[k]; ++s) {
+        const unsigned int m = marg[s_moff[k] + s];
+        if (static_cast<unsigned long long>(m) * p.nb[k] >= th) { if (first < 0) first = s; last = s; }
+        if (m > best) { best = m; arg = s; }
+      }
+      if (first < 0) { first = last = arg; }
+      lo[k] = first; len[k] = last - first + 1; vol *= len[k];
+    }
+    // shrink if a degenerate threshold left the box above budget (cannot happen for th = s_hi, kept for safety)
+    while (vol > budget) {
+      int kb = 0; for (int k = 1; k < K; ++k) if (len[k] > len[kb]) kb = k;
+      vol = vol / len[kb] * (len[kb] - 1); len[kb] -= 1;
+    }
+    // greedy growth: add the neighbouring slice with the largest probe mass per added bin while it fits
+    while (true) {
+      int bk = -1, bside = 0; double bgain = -1.0;
+      for (int k = 0; k < K; ++k) {
+        const long long nv = vol / len[k] * (len[k] + 1);
+        if (nv > budget) continue;
+        if (lo[k] > 0) { double g = (static_cast<double>(marg[s_moff[k] + lo[k] - 1]) + 1e-3) * len[k]; if (g > bgain) { bgain = g; bk = k; bside = -1; } }
+        if (lo[k] + len[k] < p.nb[k]) { double g = (static_cast<double>(marg[s_moff[k] + lo[k] + len[k]]) + 1e-3) * len[k]; if (g > bgain) { bgain = g; bk = k; bside = 1; } }
+      }
+      if (bk < 0) break;
+      vol = vol / len[bk] * (len[bk] + 1);
+      if (bside < 0) lo[bk] -= 1;
+      len[bk] += 1;
+    }
+    for (int k = 0; k < XHK_MAX_VARS; ++k) { wout->lo[k] = k < K ? lo[k] : 0; wout->len[k] = k < K ? len[k] : 0; }
+  }
+}
+
+// zero the rows of `out` that are shared between CTAs under the sample partition (XHK_FULL only)
+template <typename OT>
+__global__ void k_zero_shared_rows(const __grid_constant__ XhkParams p, int hist_grid) {
+  const long long total = p.M * p.N;
+  long long row = -1;
+  if (p.M == 1) { if (blockIdx.x == 0) row = 0; }
+  else if (blockIdx.x >= 1 && blockIdx.x < hist_grid) {
+    const long long s = blockIdx.x * p.per_cta;
+    if (s < total && (s % p.N) != 0) {
+      row = s / p.N;
+      const long long sp = (blockIdx.x - 1ll) * p.per_cta;         // previous boundary
+      if (sp > row * p.N) row = -1;                                 // an earlier boundary already clears this row
+    }
+  }
+  if (row < 0) return;
+  OT* o = static_cast<OT*>(p.out) + row * p.B;
+  for (long long b = threadIdx.x; b < p.B; b += blockDim.x) o[b] = OT(0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// utilities: counter-based synthetic data, min/max, L2 flush
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+template <typename T, int NORMAL>
+__global__ void k_fill(T* p, long long n, unsigned long long seed, long long offset) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long h = mix64(mix64(seed) ^ static_cast<unsigned long long>(offset + i));
+    if (NORMAL) {
+      // Box-Muller on two 24/32-bit uniforms; only needs to be reproducible on the device
+      const double u1 = (static_cast<double>(h >> 32) + 1.0) * (1.0 / 4294967297.0);
+      const double u2 = static_cast<double>(h & 0xFFFFFFFFull) * (1.0 / 4294967296.0);
+      p[i] = static_cast<T>(sqrt(-2.0 * log(u1)) * cospi(2.0 * u2));
+    } else {
+      if (sizeof(T) == 4) p[i] = static_cast<T>(static_cast<float>(h >> 40) * (1.0f / 16777216.0f));
+      else p[i] = static_cast<T>(static_cast<double>(h >> 11) * (1.0 / 9007199254740992.0));
+    }
+  }
+}
+
+template <typename T>
+__global__ void k_minmax(const T* __restrict__ d, long long n, double* out /* [grid][3] */) {
+  double mn = INFINITY, mx = -INFINITY; int nan = 0;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double v = static_cast<double>(d[i]);
+    if (v != v) nan = 1; else { mn = fmin(mn, v); mx = fmax(mx, v); }
+  }
+  __shared__ double smn[32], smx[32]; __shared__ int snan[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { smn[w] = mn; smx[w] = mx; snan[w] = nan; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (blockDim.x >> 5); ++i) { mn = fmin(mn, smn[i]); mx = fmax(mx, smx[i]); nan |= snan[i]; }
+    out[3 * blockIdx.x + 0] = mn; out[3 * blockIdx.x + 1] = mx; out[3 * blockIdx.x + 2] = nan ? 1.0 : 0.0;
+  }
+}
+
+__global__ void k_flush(uint4* buf, size_t n16) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) buf[i] = make_uint4(i, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------------
+typedef void (*HistKernel)(const XhkParams);
+
+template <typename T, int W>
+HistKernel pick_k(int K) {
+  switch (K) {
+    case 1: return k_hist<T, W, 1>;
+    case 2: return k_hist<T, W, 2>;
+    case 3: return k_hist<T, W, 3>;
+    case 4: return k_hist<T, W, 4>;
+    default: return k_hist<T, W, 0>;
+  }
+}
+
+HistKernel pick(int dtype, int w_dtype, int K) {
+  if (dtype == 1) {
+    if (w_dtype == 0) return pick_k<float, 0>(K);
+    if (w_dtype == 1) return pick_k<float, 1>(K);
+    return pick_k<float, 2>(K);
+  }
+  if (w_dtype == 0) return pick_k<double, 0>(K);
+  if (w_dtype == 1) return pick_k<double, 1>(K);
+  return pick_k<double, 2>(K);
+}
+
+}  // namespace
+
+cudaError_t xhk_set_smem_limits(int max_optin) {
+  for (int dt = 1; dt <= 2; ++dt)
+    for (int w = 0; w <= 2; ++w)
+      for (int k = 1; k <= 5; ++k) {
+        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick(dt, w, k)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+        if (e != cudaSuccess) return e;
+      }
+  // k_window has a little more static shared memory than k_hist
+  cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k_window<float>), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 192);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(reinterpret_cast<const void*>(k_window<double>), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 192);
+}
+
+cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l) {
+  HistKernel k = pick(l.dtype, l.w_dtype, p.n_vars);
+  k<<<l.grid, l.threads, l.smem_bytes, l.stream>>>(p);
+  return cudaGetLastError();
+}
+
+size_t xhk_window_kernel_smem(const XhkParams& p) {
+  size_t tsz = 8;  // upper bound on sizeof(T)
+  size_t e = (static_cast<size_t>(p.n_edges_total) * tsz + 15) & ~static_cast<size_t>(15);
+  size_t m = 0; for (int k = 0; k < p.n_vars; ++k) m += static_cast<size_t>(p.nb[k]) * 4;
+  return e + m;
+}
+
+cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow* window_dev, int budget_bins, int n_probe) {
+  const size_t smem = xhk_window_kernel_smem(p);
+  if (l.dtype == 1) k_window<float><<<1, kMaxThreads, smem, l.stream>>>(p, window_dev, budget_bins, n_probe);
+  else k_window<double><<<1, kMaxThreads, smem, l.stream>>>(p, window_dev, budget_bins, n_probe);
+  return cudaGetLastError();
+}
+
+cudaError_t xhk_launch_zero_shared_rows(const XhkParams& p, const XhkLaunch& l) {
+  if (l.w_dtype == 0) k_zero_shared_rows<unsigned long long><<<l.grid, 256, 0, l.stream>>>(p, l.grid);
+  else k_zero_shared_rows<double><<<l.grid, 256, 0, l.stream>>>(p, l.grid);
+  return cudaGetLastError();
+}
+
+cudaError_t xhk_launch_fill(void* ptr, int dtype, long long n, unsigned long long seed, long long offset, int normal, cudaStream_t s) {
+  const int grid = 148 * 8, thr = 256;
+  if (dtype == 1) { if (normal) k_fill<float, 1><<<grid, thr, 0, s>>>(static_cast<float*>(ptr), n, seed, offset); else k_fill<float, 0><<<grid, thr, 0, s>>>(static_cast<float*>(ptr), n, seed, offset); }
+  else { if (normal) k_fill<double, 1><<<grid, thr, 0, s>>>(static_cast<double*>(ptr), n, seed, offset); else k_fill<double, 0><<<grid, thr, 0, s>>>(static_cast<double*>(ptr), n, seed, offset); }
+  return cudaGetLastError();
+}
+
+cudaError_t xhk_launch_minmax(const void* data, int dtype, long long n, double* out_dev, cudaStream_t s) {
+  const int grid = 296, thr = 256;  // out_dev holds grid*3 doubles
+  if (dtype == 1) k_minmax<float><<<grid, thr, 0, s>>>(static_cast<const float*>(data), n, out_dev);
+  else k_minmax<double><<<grid, thr, 0, s>>>(static_cast<const double*>(data), n, out_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t xhk_launch_flush(void* buf, size_t bytes, cudaStream_t s) {
+  k_flush<<<148 * 4, 512, 0, s>>>(static_cast<uint4*>(buf), bytes / 16);
+  return cudaGetLastError();
+}

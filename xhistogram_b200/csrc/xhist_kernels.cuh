@@ -1,0 +1,78 @@
+// xhist_kernels.cuh — shared declarations between the kernels (xhist_kernels.cu) and the
+// host side of the C-ABI (xhist_api.cu).  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define XHK_MAX_VARS 8
+
+// How the per-CTA shared-memory histogram is used.
+enum XhkHistMode {
+  XHK_GLOBAL = 0,  // no shared histogram: every sample goes to a global RED (huge bin spaces / testing)
+  XHK_FULL = 1,    // the whole (prod nb) bin space of one row is privatised in shared memory
+  XHK_WINDOW = 2   // a hyper-rectangular window of the bin space is privatised; the rest spills to global RED
+};
+
+// How rows/samples are split over the persistent CTAs.
+enum XhkPartition {
+  XHK_PART_SAMPLES = 0,  // equal contiguous ranges of the flattened (M*N) sample space
+  XHK_PART_ROWS = 1      // whole rows per CTA (no row is shared between CTAs -> no zero-fill, no atomics)
+};
+
+// Device-chosen window (written by the window kernel, read by the histogram kernel).
+struct XhkWindow {
+  int lo[XHK_MAX_VARS];
+  int len[XHK_MAX_VARS];
+};
+
+// Kernel parameters (passed by value, lives in the constant bank).
+// T-typed classification constants are stored as raw 8-byte slots (float kernels read the low 4 bytes).
+struct XhkParams {
+  const void* data[XHK_MAX_VARS];
+  long long stride[XHK_MAX_VARS];   // row stride in elements (0 = broadcast row)
+  const void* w;
+  long long wstride;
+  // classification constants, typed T (float or double) in the first sizeof(T) bytes of each slot
+  double lo[XHK_MAX_VARS];          // smallest in-range value  (effective first edge)
+  double hi[XHK_MAX_VARS];          // largest in-range value   (effective last edge)
+  double e0[XHK_MAX_VARS];          // uniform path: t = (x - e0) * inv
+  double inv[XHK_MAX_VARS];
+  double delta[XHK_MAX_VARS];       // uniform path: bin certain iff delta <= frac(t) <= omd
+  double omd[XHK_MAX_VARS];
+  int nb[XHK_MAX_VARS];             // bins of variable k  (= n_edges - 1)
+  int uniform[XHK_MAX_VARS];        // 1: uniform fast path usable for variable k
+  int eoff[XHK_MAX_VARS];           // offset of variable k's effective edges in `edges`
+  long long gmul[XHK_MAX_VARS];     // C-order multipliers of the global bin index
+  const void* edges;                // device, typed T, all variables concatenated
+  int n_edges_total;
+  int n_vars;
+  void* out;                        // int64 (no weights) or double (weights), [M][B]
+  long long B;                      // bins per row
+  long long M, N;
+  int hist_mode;                    // XhkHistMode
+  int partition;                    // XhkPartition
+  int hist_capacity;                // shared histogram capacity in bins
+  int store_owned_rows;             // 1: a row wholly owned by one CTA is written with plain stores
+  const XhkWindow* window;          // XHK_WINDOW: device-chosen window
+  int wlo[XHK_MAX_VARS];            // XHK_FULL: 0 / nb ; ignored otherwise
+  int wlen[XHK_MAX_VARS];
+  long long per_cta;                // XHK_PART_SAMPLES: samples per CTA (multiple of 1024)
+};
+
+struct XhkLaunch {
+  int dtype;       // 1 f32, 2 f64 (xh_dtype)
+  int w_dtype;     // 0 none, 1 f32, 2 f64
+  int grid, threads;
+  size_t smem_bytes;
+  cudaStream_t stream;
+};
+
+// host-callable launchers (defined in xhist_kernels.cu)
+cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l);
+cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow* window_dev, int budget_bins, int n_probe);
+cudaError_t xhk_launch_zero_shared_rows(const XhkParams& p, const XhkLaunch& l);
+cudaError_t xhk_set_smem_limits(int max_optin);
+cudaError_t xhk_launch_fill(void* ptr, int dtype, long long n, unsigned long long seed, long long offset, int normal, cudaStream_t s);
+cudaError_t xhk_launch_minmax(const void* data, int dtype, long long n, double* out2_dev, cudaStream_t s);
+cudaError_t xhk_launch_flush(void* buf, size_t bytes, cudaStream_t s);
+size_t xhk_window_kernel_smem(const XhkParams& p);

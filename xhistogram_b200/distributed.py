@@ -1,0 +1,180 @@
+"""One-rank-per-GPU histograms: shard, histogram locally on the GPU, combine the partials.
+
+This replaces the role dask plays in the reference — ``blockwise(_bincount)`` over chunks followed
+by ``.sum`` over the chunked axes (xhistogram/core.py:403-439):
+
+* the sharded axis is REDUCED (flat 1e9-sample histograms): every rank builds a partial
+  histogram of its slab and the partials are summed with one all-reduce (NCCL inside
+  ``libxhist_b200.so``: ``xh_comm_allreduce``; int64 counts stay bit-exact, float64 sums differ
+  only by add order);
+* the sharded axis is KEPT (e.g. ``time`` in the (time, lat, lon) case): rows are independent,
+  every rank owns a disjoint slab of the output and no reduction is needed (an optional
+  all-gather assembles the full array).
+
+``Communicator`` is the small interface the algorithm needs.  ``NcclCommunicator`` is the product
+implementation (library-owned NCCL communicator, bootstrapped by broadcasting the 128-byte
+unique id through any out-of-band channel, e.g. ``torch.distributed``);
+``TorchCommunicator`` runs the same algorithm over ``torch.distributed`` tensors and is what the
+world-size-2 ``gloo`` CPU tests use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+
+import numpy as np
+
+from . import _cabi
+from . import core as _core
+
+_range = range
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous, balanced [start, stop) of ``n`` items for ``rank`` of ``world``."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+class Communicator:
+    rank = 0
+    world = 1
+
+    def allreduce_sum(self, a: np.ndarray) -> np.ndarray:  # int64 or float64
+        return a
+
+    def allreduce_minmax(self, mn: float, mx: float):
+        return mn, mx
+
+    def allgather_rows(self, a: np.ndarray, counts) -> np.ndarray:  # concatenate along axis 0
+        return a
+
+
+class TorchCommunicator(Communicator):
+    """``torch.distributed`` plumbing (any backend).  CPU tensors for gloo, CUDA tensors for nccl."""
+
+    def __init__(self, device=None):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self._device = device
+
+    def _t(self, a):
+        import torch
+
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(self._device) if self._device is not None else t
+
+    def allreduce_sum(self, a):
+        t = self._t(a)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def allreduce_minmax(self, mn, mx):
+        t = self._t(np.array([-mn, mx], dtype=np.float64))  # NaN propagates through MAX on both backends
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX)
+        v = t.cpu().numpy()
+        return -float(v[0]), float(v[1])
+
+    def allgather_rows(self, a, counts):
+        import torch
+
+        t = self._t(a)
+        outs = [torch.empty((int(c),) + tuple(a.shape[1:]), dtype=t.dtype, device=t.device) for c in counts]
+        self._dist.all_gather(outs, t) if len(set(int(c) for c in counts)) == 1 else self._uneven(outs, t)
+        return torch.cat(outs).cpu().numpy()
+
+    def _uneven(self, outs, t):
+        for r, o in enumerate(outs):
+            if r == self.rank:
+                o.copy_(t)
+            self._dist.broadcast(o, src=r)
+
+
+class NcclCommunicator(Communicator):
+    """NCCL communicator owned by ``libxhist_b200.so`` (one rank per GPU, NVLink/NVSwitch)."""
+
+    def __init__(self, device: int, rank: int, world: int, unique_id: bytes):
+        self.device, self.rank, self.world = int(device), int(rank), int(world)
+        buf = C.create_string_buffer(unique_id, _cabi.XH_NCCL_UNIQUE_ID_BYTES)
+        _cabi.check(_cabi.lib().xh_comm_init_rank(self.device, buf, self.world, self.rank), "xh_comm_init_rank")
+
+    @staticmethod
+    def create_unique_id() -> bytes:
+        buf = C.create_string_buffer(_cabi.XH_NCCL_UNIQUE_ID_BYTES)
+        _cabi.check(_cabi.lib().xh_comm_unique_id(buf), "xh_comm_unique_id")
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, device: int):
+        """Bootstrap over an initialised ``torch.distributed`` group (used only to ship the id)."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.create_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(device, rank, world, box[0])
+
+    def allreduce_device(self, ptr: int, count: int, is_f64: bool):
+        _cabi.check(_cabi.lib().xh_comm_allreduce(self.device, ptr, count, 1 if is_f64 else 0), "xh_comm_allreduce")
+
+    def allreduce_sum(self, a):
+        from .device import DeviceArray
+
+        is_f64 = a.dtype == np.float64
+        d = DeviceArray.from_numpy(a.view(np.float64) if not is_f64 else a, device=self.device)
+        self.allreduce_device(d.ptr, a.size, is_f64)
+        out = d.to_numpy()
+        d.free()
+        return out if is_f64 else out.view(np.int64)
+
+    def allreduce_minmax(self, mn, mx):
+        raise NotImplementedError("pass explicit bin edges (or a range) with the NCCL communicator")
+
+    def close(self):
+        _cabi.check(_cabi.lib().xh_comm_destroy(self.device), "xh_comm_destroy")
+
+
+def histogram(*local_args, bins=None, range=None, axis=None, weights=None, density=False, block_size="auto",
+              comm: Communicator = None, sharded_axis=0, gather=False):
+    """SPMD histogram: every rank passes ITS shard of the arrays (split along ``sharded_axis``).
+
+    Same arguments as ``core.histogram`` otherwise.  Returns ``(h, edges)``; when the sharded axis
+    is reduced ``h`` is the global histogram on every rank, when it is kept ``h`` is this rank's
+    slab (or the assembled array with ``gather=True``).
+    """
+    comm = comm or Communicator()
+    a0 = local_args[0]
+    nd = np.ndim(a0) if not _core.is_device_array(a0) else len(_core.as_device_view(a0)[1])
+    sharded_axis = sharded_axis if sharded_axis >= 0 else nd + sharded_axis
+    if axis is None:
+        red = list(_range(nd))
+    else:
+        red = [int(a) if a >= 0 else nd + int(a) for a in np.atleast_1d(axis)]
+    n = len(local_args)
+    bins_l = _core._ensure_correctly_formatted_bins(bins, n)
+    range_l = _core._ensure_correctly_formatted_range(range, n)
+    edges = []
+    for a, b, r in zip(local_args, bins_l, range_l):
+        if isinstance(b, str):
+            raise TypeError("distributed histograms need explicit bin edges or an integer bin count")
+        if np.ndim(b) == 0 and r is None:
+            mn, mx = comm.allreduce_minmax(*_core._minmax(a))      # global range, then numpy's own edge formula
+            dt = _core.as_device_view(a)[2] if _core.is_device_array(a) else np.asarray(a).dtype
+            edges.append(np.histogram_bin_edges(np.array([mn, mx], dtype=dt), bins=b))
+        else:
+            edges.append(_core._resolve_edges(a if _core.is_device_array(a) else np.asarray(a), b, r, None))
+    h, _ = _core.histogram(*local_args, bins=edges, axis=axis, weights=weights, density=False, block_size=block_size)
+    if sharded_axis in red:
+        h = comm.allreduce_sum(np.ascontiguousarray(h))             # partial histograms -> global (core.py:439)
+    elif gather:
+        kept = [i for i in _range(nd) if i not in red]
+        pos = kept.index(sharded_axis)
+        hm = np.ascontiguousarray(np.moveaxis(h, pos, 0))
+        counts = comm.allreduce_sum(np.eye(comm.world, dtype=np.int64)[comm.rank] * hm.shape[0])
+        h = np.moveaxis(comm.allgather_rows(hm, counts), 0, pos)
+    if density:                                                     # after the reduce, on O(bins) data (core.py:444-462)
+        areas = functools.reduce(np.multiply.outer, [np.diff(e) for e in edges])
+        bin_axes = tuple(_range(-n, 0))
+        h = h / areas / h.sum(axis=bin_axes, keepdims=True)
+    return h, edges

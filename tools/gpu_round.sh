@@ -1,0 +1,15 @@
+#!/bin/bash
+# One GPU session: bench line, ncu launch list (shares), ncu --set full capture of k_hist.
+# usage (under gpurun): bash tools/gpu_round.sh <tag>
+TAG=${1:-r1}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+tail -c 3000 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 1 --samples 2.5e8 > gpurun_out/${TAG}_ncu_launch.log 2>&1
+tail -3 gpurun_out/${TAG}_ncu_launch.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_hist -s 5 -c 1 -f -o gpurun_out/${TAG}_prof_hist \
+    python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/${TAG}_ncu_full.log 2>&1
+tail -3 gpurun_out/${TAG}_ncu_full.log
+ls -la gpurun_out | tail -12

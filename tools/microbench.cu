@@ -80,7 +80,9 @@ enum Mode {
   M_SUM = 0, M_BIN = 1, M_GRED_F64 = 2, M_GRED_U64 = 3, M_GRED_U32 = 4,
   M_SMEM_U32 = 5, M_SMEM_F32 = 6, M_SMEM_F64 = 7, M_BSEARCH_GRED_F64 = 8, M_GRED_F32 = 9,
   M_SMEM_U32_NOW = 10,  // counts, do not read weights (8 B/sample)
-  M_BIN_NOW = 11, M_SUM_NOW = 12, M_GRED_U64_NOW = 13, M_BSEARCH_NOW = 14
+  M_BIN_NOW = 11, M_SUM_NOW = 12, M_GRED_U64_NOW = 13, M_BSEARCH_NOW = 14,
+  M_SMEM_FIX2 = 15,  // exact 64-bit fixed point in two u32 limbs (lo with carry-out, hi)
+  M_SMEM_FIX1 = 16   // 32-bit fixed point + carry counter
 };
 
 struct Args {
@@ -118,20 +120,39 @@ __device__ __forceinline__ void accumulate(const Args& a, const float* sedges, v
   else if (MODE == M_SMEM_U32_NOW) { atomicAdd((unsigned*)shist + bin, 1u); }
   else if (MODE == M_SMEM_F32) atomicAdd((float*)shist + bin, w);
   else if (MODE == M_SMEM_F64) atomicAdd((double*)shist + bin, (double)w);
+  else if (MODE == M_SMEM_FIX2) {
+    const float vs = w * 1099511627776.0f;            // 2^40
+    const long long v = __float2ll_rn(vs);
+    if ((float)v == vs) {                              // exactly representable -> integer accumulation is exact
+      const unsigned lo = (unsigned)v; unsigned hi = (unsigned)(v >> 32);
+      const unsigned old = atomicAdd((unsigned*)shist + bin, lo);
+      hi += ((old + lo) < old) ? 1u : 0u;
+      if (hi) atomicAdd((unsigned*)shist + B + bin, hi);
+    } else atomicAdd((double*)a.out + bin, (double)w);
+  } else if (MODE == M_SMEM_FIX1) {
+    const float vs = w * 1073741824.0f;               // 2^30
+    const int v = __float2int_rn(vs);
+    if ((float)v == vs) {
+      const unsigned lo = (unsigned)v;
+      const unsigned old = atomicAdd((unsigned*)shist + bin, lo);
+      unsigned hi = (v < 0 ? 0xffffffffu : 0u) + (((old + lo) < old) ? 1u : 0u);
+      if (hi) atomicAdd((unsigned*)shist + B + bin, hi);
+    } else atomicAdd((double*)a.out + bin, (double)w);
+  }
 }
 
 template <int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_hist(Args a) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr bool NOW = (MODE == M_SMEM_U32_NOW || MODE == M_BIN_NOW || MODE == M_SUM_NOW || MODE == M_GRED_U64_NOW || MODE == M_BSEARCH_NOW);
-  constexpr bool SMEMH = (MODE == M_SMEM_U32 || MODE == M_SMEM_F32 || MODE == M_SMEM_F64 || MODE == M_SMEM_U32_NOW);
+  constexpr bool SMEMH = (MODE == M_SMEM_U32 || MODE == M_SMEM_F32 || MODE == M_SMEM_F64 || MODE == M_SMEM_U32_NOW || MODE == M_SMEM_FIX1 || MODE == M_SMEM_FIX2);
   const int nE = a.px.nb + 1 + a.py.nb + 1;
   float* sedges = (float*)smem;
   void* shist = smem + ((nE * 4 + 15) & ~15);
   for (int i = threadIdx.x; i < nE; i += THREADS) sedges[i] = a.edges[i];
   const size_t B = (size_t)a.px.nb * a.py.nb;
   if (SMEMH) {
-    size_t words = (MODE == M_SMEM_F64) ? B * 2 : B;
+    size_t words = (MODE == M_SMEM_F64 || MODE == M_SMEM_FIX1 || MODE == M_SMEM_FIX2) ? B * 2 : B;
     for (size_t i = threadIdx.x; i < words; i += THREADS) ((unsigned*)shist)[i] = 0u;
   }
   __syncthreads();
@@ -180,6 +201,12 @@ __global__ void __launch_bounds__(THREADS) k_hist(Args a) {
       for (size_t b = threadIdx.x; b < B; b += THREADS) { unsigned v = ((unsigned*)shist)[b]; if (v) atomicAdd((unsigned long long*)a.out + b, (unsigned long long)v); }
     } else if (MODE == M_SMEM_F32) {
       for (size_t b = threadIdx.x; b < B; b += THREADS) { float v = ((float*)shist)[b]; if (v != 0.f) atomicAdd((double*)a.out + b, (double)v); }
+    } else if (MODE == M_SMEM_FIX1 || MODE == M_SMEM_FIX2) {
+      const double sc = (MODE == M_SMEM_FIX2) ? 1.0 / 1099511627776.0 : 1.0 / 1073741824.0;
+      for (size_t b = threadIdx.x; b < B; b += THREADS) {
+        long long v = (long long)(((unsigned long long)((unsigned*)shist)[B + b] << 32) | ((unsigned*)shist)[b]);
+        if (v) atomicAdd((double*)a.out + b, (double)v * sc);
+      }
     } else {
       for (size_t b = threadIdx.x; b < B; b += THREADS) { double v = ((double*)shist)[b]; if (v != 0.0) atomicAdd((double*)a.out + b, v); }
     }
@@ -330,7 +357,7 @@ static void run_direct(const char* tag, int nb, int ctas_per_sm, int replicas, i
   size_t B = (size_t)nb * nb;
   size_t smem = ((2 * (nb + 1) * 4 + 15) & ~15);
   if (MODE == M_SMEM_U32 || MODE == M_SMEM_F32 || MODE == M_SMEM_U32_NOW) smem += B * 4;
-  if (MODE == M_SMEM_F64) smem += B * 8;
+  if (MODE == M_SMEM_F64 || MODE == M_SMEM_FIX1 || MODE == M_SMEM_FIX2) smem += B * 8;
   if (smem > 227 * 1024) { printf("%-58s skipped (smem %zu)\n", tag, smem); return; }
   CK(cudaFuncSetAttribute(k_hist<MODE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hist<MODE, THREADS>, THREADS, smem));
@@ -392,6 +419,29 @@ int main(int argc, char** argv) {
   };
 
   printf("n = 2^%d = %zu samples; x,y ~ N(0,1) fp32, w ~ U[0,1) fp32\n", lg, n);
+  if (argc > 2 && !strcmp(argv[2], "fix")) {
+    // exact fixed-point accumulation (native u32 shared atomics) against the f64 CAS loop
+    for (int nb : {100, 128, 160}) {
+      set_edges(nb);
+      run_direct<M_SMEM_F64, 1024>("smem f64 CAS (12B)", nb, 1, 1, 12);
+      run_direct<M_SMEM_FIX2, 1024>("smem fixed 2x u32 (12B)", nb, 1, 1, 12);
+      run_direct<M_SMEM_FIX1, 1024>("smem fixed u32+carry (12B)", nb, 1, 1, 12);
+      run_direct<M_SMEM_U32, 1024>("smem u32 cnt + w read (12B)", nb, 1, 1, 12);
+      run_direct<M_SMEM_FIX2, 512>("smem fixed 2x u32 (12B)", nb, 2, 1, 12);
+      run_direct<M_SMEM_FIX1, 512>("smem fixed u32+carry (12B)", nb, 2, 1, 12);
+    }
+    // verify the fixed-point result against the f64 result (same data): total weight
+    set_edges(128);
+    std::vector<double> h1(128 * 128), h2(128 * 128);
+    { Args a = g_args; a.px = make_uparams(128, -4.f, 4.f); a.py = a.px; size_t smem = ((2 * 129 * 4 + 15) & ~15) + 128 * 128 * 8;
+      CK(cudaFuncSetAttribute(k_hist<M_SMEM_F64, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CK(cudaFuncSetAttribute(k_hist<M_SMEM_FIX2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CK(cudaMemset(g_out, 0, 128 * 128 * 8)); k_hist<M_SMEM_F64, 1024><<<148, 1024, smem>>>(a); CK(cudaMemcpy(h1.data(), g_out, h1.size() * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemset(g_out, 0, 128 * 128 * 8)); k_hist<M_SMEM_FIX2, 1024><<<148, 1024, smem>>>(a); CK(cudaMemcpy(h2.data(), g_out, h2.size() * 8, cudaMemcpyDeviceToHost));
+      size_t diff = 0; double s1 = 0, s2 = 0; for (size_t i = 0; i < h1.size(); ++i) { diff += h1[i] != h2[i]; s1 += h1[i]; s2 += h2[i]; }
+      printf("fixed-point vs f64: %zu of %zu bins differ; totals %.17g %.17g\n", diff, h1.size(), s1, s2); }
+    return 0;
+  }
   set_edges(256);
   printf("--- streaming / classification only\n");
   run_direct<M_SUM, 256>("sum x+y+w (12B)", 256, 8, 1, 12);

@@ -197,7 +197,7 @@ def _rows_view(a, axis, full):
 
 
 def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, block_size=None,
-              _devices=None, _flags=0, _timing=None):
+              _devices=None, _flags=0, _timing=None, _out_device=None):
     """GPU replacement of the reference's ``_bincount`` (core.py:197-247).
 
     Same contract: ``all_arrays`` are mutually broadcast arrays of identical shape (weights last
@@ -232,7 +232,9 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
             N = int(np.prod(shape[nd - len(axis):], dtype=np.int64))
             M = int(np.prod(shape[: nd - len(axis)], dtype=np.int64))
         dev = views[0][3]
-        out = _device_call(views, wview, bins, M, N, dev, _flags, _timing)
+        out = _device_call(views, wview, bins, M, N, dev, _flags, _timing, _out_device)
+        if _out_device is not None:
+            return out                                       # DeviceArray (M * prod(bins)), stays in HBM
         return out.reshape(kept_axes_shape + nbins)
 
     data = [_as_float_data(np.asarray(a)) for a in all_arrays]
@@ -256,15 +258,15 @@ def _host_call(arrs, strides, wrow, bins, M, N, xdt, devices, flags, timing):
                       devices[0] if devices else _default_device(), devices, flags, timing)
 
 
-def _device_call(views, wview, bins, M, N, dev, flags, timing):
+def _device_call(views, wview, bins, M, N, dev, flags, timing, out_device=None):
     ptrs = [v[0] for v in views]
     wptr = wview[0] if wview else None
     wdt = _xh_dtype(wview[2]) if wview else _cabi.XH_NONE
     return _desc_call(ptrs, [N] * len(ptrs), wptr, N if wview else 0, bins, M, N, _xh_dtype(views[0][2]), wdt,
-                      _cabi.XH_DEVICE, dev, None, flags, timing)
+                      _cabi.XH_DEVICE, dev, None, flags, timing, out_device)
 
 
-def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing):
+def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing, out_device=None):
     K = len(arrs)
     if K > _cabi.XH_MAX_VARS:
         raise NotImplementedError(f"at most {_cabi.XH_MAX_VARS} variables are supported")
@@ -288,11 +290,17 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
         if mem == _cabi.XH_HOST and not w.size:
             d.w_dtype = _cabi.XH_NONE
     B = int(np.prod([len(b) - 1 for b in bins], dtype=np.int64))
-    out = np.empty((M, B), dtype=np.int64 if w is None else np.float64)
-    if M * N == 0 or B == 0:
-        out[...] = 0
-        return out
-    d.out = out.ctypes.data
+    if out_device is not None:
+        if out_device.size != M * B or out_device.dtype.itemsize != 8:
+            raise ValueError("device output buffer has the wrong size")
+        out = out_device
+        d.out, d.out_mem = out_device.ptr, _cabi.XH_DEVICE
+    else:
+        out = np.empty((M, B), dtype=np.int64 if w is None else np.float64)
+        if M * N == 0 or B == 0:
+            out[...] = 0
+            return out
+        d.out = out.ctypes.data
     ms = C.c_float(0.0)
     if timing is not None:
         d.kernel_ms = C.pointer(ms)

@@ -145,7 +145,9 @@ int get_ctx(int device, Ctx** out) {
 float up32(double e) { float f = static_cast<float>(e); if (static_cast<double>(f) < e) f = std::nextafterf(f, INFINITY); return f; }
 float dn32(double e) { float f = static_cast<float>(e); if (static_cast<double>(f) > e) f = std::nextafterf(f, -INFINITY); return f; }
 
-template <typename T> void put_slot(double& s, T v) { s = 0.0; std::memcpy(&s, &v, sizeof(T)); }
+template <typename T> struct CSel;
+template <> struct CSel<float> { static float* row(XhkParams& p, int k) { return p.cf[k]; } };
+template <> struct CSel<double> { static double* row(XhkParams& p, int k) { return p.cd[k]; } };
 
 // Fill the classification constants of variable k; append its effective edges to `table`.
 template <typename T>
@@ -158,9 +160,10 @@ int prep_var(const double* e, int E, int k, bool force_search, XhkParams& p, std
   for (int j = 0; j < E; ++j) table.push_back(f32 ? static_cast<T>(up32(e[j])) : static_cast<T>(e[j]));
   const T lo = table[p.eoff[k]];
   const T hi = f32 ? static_cast<T>(dn32(e[E - 1])) : static_cast<T>(e[E - 1]);
-  put_slot<T>(p.lo[k], lo); put_slot<T>(p.hi[k], hi);
+  T* c = CSel<T>::row(p, k);
+  c[XHK_C_LO] = lo; c[XHK_C_HI] = hi;
   p.uniform[k] = 0;
-  put_slot<T>(p.e0[k], T(0)); put_slot<T>(p.inv[k], T(0)); put_slot<T>(p.delta[k], T(2)); put_slot<T>(p.omd[k], T(-1));
+  c[XHK_C_E0] = T(0); c[XHK_C_INV] = T(0); c[XHK_C_DELTA] = T(2); c[XHK_C_OMD] = T(-1);
   if (force_search) return XH_OK;
   // uniform fast path: usable when the edges are an arithmetic progression up to a small, bounded deviation
   const long double e0 = e[0], eN = e[E - 1];
@@ -185,7 +188,7 @@ int prep_var(const double* e, int E, int k, bool force_search, XhkParams& p, std
   // round delta up and 1-delta down in T
   T dT = static_cast<T>(static_cast<double>(delta)); if (static_cast<long double>(dT) < delta) dT = std::nextafter(dT, T(1));
   T oT = static_cast<T>(static_cast<double>(1.0L - delta)); if (static_cast<long double>(oT) > 1.0L - delta) oT = std::nextafter(oT, T(0));
-  put_slot<T>(p.e0[k], e0T); put_slot<T>(p.inv[k], invT); put_slot<T>(p.delta[k], dT); put_slot<T>(p.omd[k], oT);
+  c[XHK_C_E0] = e0T; c[XHK_C_INV] = invT; c[XHK_C_DELTA] = dT; c[XHK_C_OMD] = oT;
   p.uniform[k] = 1;
   return XH_OK;
 }
@@ -205,6 +208,7 @@ struct Prep {
   XhkParams base;
   std::vector<unsigned char> edge_host;
   size_t edges_al = 0;
+  mutable bool window_done = false;   // the shared-memory window is chosen on the first block of a call and reused
 };
 
 int prep_call(const xh_desc* d, Prep& pr) {
@@ -226,6 +230,8 @@ int prep_call(const xh_desc* d, Prep& pr) {
     B *= p.nb[k];
   }
   p.B = B;
+  p.all_uniform = 1;
+  for (int k = 0; k < K; ++k) p.all_uniform = p.all_uniform && p.uniform[k];
   long long mul = 1;
   for (int k = K - 1; k >= 0; --k) { p.gmul[k] = mul; mul *= p.nb[k]; }
   p.n_edges_total = static_cast<int>(d->dtype == XH_F32 ? tf.size() : td.size());
@@ -314,15 +320,16 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
 }
 
 // Enqueue zero-fill, window selection and the histogram kernel of one planned block.
-int enqueue(Ctx* c, Plan& pl) {
+int enqueue(Ctx* c, const Prep& pr, Plan& pl) {
   cudaStream_t s = pl.l.stream;
   const size_t osz = 8;
   if (pl.zero == Plan::ZERO_ALL) CU(cudaMemsetAsync(pl.p.out, 0, static_cast<size_t>(pl.p.M) * pl.p.B * osz, s));
   else if (pl.zero == Plan::ZERO_SHARED) CU(xhk_launch_zero_shared_rows(pl.p, pl.l));
-  if (pl.need_window) {
+  if (pl.need_window && !pr.window_done) {
     const long long total = pl.p.M * pl.p.N;
-    const int n_probe = static_cast<int>(std::min<long long>(total, 1 << 16));
+    const int n_probe = static_cast<int>(std::min<long long>(total, 1 << 14));
     CU(xhk_launch_window(pl.p, pl.l, c->window, pl.window_budget, n_probe));
+    pr.window_done = true;
   }
   CU(xhk_launch_hist(pl.p, pl.l));
   return XH_OK;
@@ -363,7 +370,7 @@ int run_device_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stre
   Plan pl;
   int rc = plan_block(c, pr, d, stream, pl);
   if (rc) return rc;
-  return enqueue(c, pl);
+  return enqueue(c, pr, pl);
 }
 
 // host inputs: double-buffered H2D pipeline feeding device blocks that accumulate into dev_out

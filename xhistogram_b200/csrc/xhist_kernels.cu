@@ -20,8 +20,13 @@ namespace {
 constexpr int kMaxThreads = 1024;
 constexpr long long kSegCap = 1ll << 30;  // u32 shared counters are flushed at least this often
 
-template <typename T>
-__device__ __forceinline__ T slot(const double& d) { return *reinterpret_cast<const T*>(&d); }
+template <typename T> struct Consts;
+template <> struct Consts<float> {
+  static __device__ __forceinline__ float get(const XhkParams& p, int k, int i) { return p.cf[k][i]; }
+};
+template <> struct Consts<double> {
+  static __device__ __forceinline__ double get(const XhkParams& p, int k, int i) { return p.cd[k][i]; }
+};
 
 __device__ __forceinline__ int floor_to_int(float t) { return __float2int_rd(t); }
 __device__ __forceinline__ int floor_to_int(double t) { return __double2int_rd(t); }
@@ -44,22 +49,33 @@ __device__ __forceinline__ int search_bin(const T* __restrict__ e, int nb, T x) 
   return b > nb - 1 ? nb - 1 : b;  // right-inclusive last bin (core.py:171-173)
 }
 
+// Uniform-edge arithmetic.  t = (x - e0) * inv is within delta/2 of the exact position of x in
+// bin units (bound computed on the host from the rounding errors and from the deviation of the
+// edges from an arithmetic progression), so j = floor(t) is THE bin whenever
+// delta <= frac(t) <= 1 - delta and 0 <= j < nb; only the other samples (~1e-4) need the search.
 template <typename T>
-__device__ __forceinline__ int classify(const XhkParams& p, int k, const T* __restrict__ sedges, T x) {
-  const T lo = slot<T>(p.lo[k]), hi = slot<T>(p.hi[k]);
-  if (!(x >= lo && x <= hi)) return -1;  // NaN compares false: dropped (rule R3)
+__device__ __forceinline__ bool uniform_guess(const XhkParams& p, int k, T x, int& j) {
+  const T t = (x - Consts<T>::get(p, k, XHK_C_E0)) * Consts<T>::get(p, k, XHK_C_INV);
+  j = floor_to_int(t);                // NaN -> 0, +-inf / huge -> saturated: both fail the tests below
+  const T f = t - static_cast<T>(j);  // NaN stays NaN: compares false
+  return (f >= Consts<T>::get(p, k, XHK_C_DELTA)) & (f <= Consts<T>::get(p, k, XHK_C_OMD));
+}
+
+// exact bin of any sample (slow but general): range test, uniform guess when usable, else search
+template <typename T>
+__device__ __forceinline__ int exact_bin_inline(const XhkParams& p, int k, const T* __restrict__ sedges, T x) {
+  if (!(x >= Consts<T>::get(p, k, XHK_C_LO) && x <= Consts<T>::get(p, k, XHK_C_HI))) return -1;  // NaN: dropped (rule R3)
   const int nb = p.nb[k];
   if (p.uniform[k]) {
-    // Evenly spaced edges: t = (x - e0) * inv is within delta/2 of the exact position in bin units
-    // (bound computed on the host from the rounding errors and the edges' deviation from the
-    // arithmetic progression), so floor(t) is the exact bin unless frac(t) is within delta of an
-    // integer; only those samples (~1e-4 of them) pay for the search.
-    const T t = (x - slot<T>(p.e0[k])) * slot<T>(p.inv[k]);
-    const int j = floor_to_int(t);
-    const T f = t - (T)j;
-    if (f >= slot<T>(p.delta[k]) && f <= slot<T>(p.omd[k]) && j >= 0 && j < nb) return j;
+    int j;
+    if (uniform_guess<T>(p, k, x, j) && static_cast<unsigned>(j) < static_cast<unsigned>(nb)) return j;
   }
   return search_bin<T>(sedges + p.eoff[k], nb, x);
+}
+// out-of-line copy for the rare exact path of the fast kernel (keeps its hot loop small)
+template <typename T>
+__device__ __noinline__ int exact_bin(const XhkParams& p, int k, const T* __restrict__ sedges, T x) {
+  return exact_bin_inline<T>(p, k, sedges, x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -80,10 +96,12 @@ template <> struct WType<2> { using type = double; };
 
 // ---------------------------------------------------------------------------------------------
 // the histogram kernel
-//   T  : data type (float / double)          W : 0 no weights, 1 fp32 weights, 2 fp64 weights
-//   KT : number of variables at compile time (1..4), or 0 = runtime p.n_vars (scalar loads only)
+//   T    : data type (float / double)        W : 0 no weights, 1 fp32 weights, 2 fp64 weights
+//   KT   : number of variables at compile time (1..4), or 0 = runtime p.n_vars (scalar loads only)
+//   FAST : every variable has evenly spaced edges -> branch-free classification of 4 samples at a
+//          time; samples that are uncertain or fall outside the shared window take a side path
 // ---------------------------------------------------------------------------------------------
-template <typename T, int W, int KT>
+template <typename T, int W, int KT, bool FAST>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__ XhkParams p) {
   using HT = typename std::conditional<W == 0, unsigned int, double>::type;          // shared accumulator
   using OT = typename std::conditional<W == 0, unsigned long long, double>::type;    // global accumulator
@@ -127,28 +145,43 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
     s1 = s0 + p.per_cta; if (s1 > total) s1 = total;
   }
 
-  // one sample: classify every variable, then add to the shared window or spill to global
-  auto sample = [&](const T (&x)[KMAX], double wv, OT* out_row) {
+  // ---- accumulation primitives ------------------------------------------------------------
+  auto global_add = [&](OT* out_row, long long gbin, double wv) {
+    if constexpr (W == 0) atomicAdd(out_row + gbin, 1ull); else atomicAdd(out_row + gbin, wv);
+  };
+  // general path of one sample: exact bins, then shared window / global spill / drop.
+  // Returns the window bin when the caller should do the shared add itself, else -1.
+  auto general_sample = [&](const T (&x)[KMAX], double wv, OT* out_row) -> int {
     int j[KMAX]; int wbin = 0; bool ok = true, inwin = true;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k < K) {
-        j[k] = classify<T>(p, k, sedges, x[k]);
+        j[k] = FAST ? exact_bin<T>(p, k, sedges, x[k]) : exact_bin_inline<T>(p, k, sedges, x[k]);
         ok = ok && (j[k] >= 0);
         const unsigned jw = static_cast<unsigned>(j[k] - wlo[k]);
-        inwin = inwin && (jw < static_cast<unsigned>(wlen[k]));  // also false for j == -1
+        inwin = inwin && (jw < static_cast<unsigned>(wlen[k]));   // also false for j == -1
         wbin = wbin * wlen[k] + static_cast<int>(jw);
       }
     }
-    if (inwin) {
-      if constexpr (W == 0) atomicAdd(reinterpret_cast<unsigned int*>(shist) + wbin, 1u);
-      else atomicAdd(reinterpret_cast<double*>(shist) + wbin, wv);
-    } else if (ok) {
+    if (inwin) return wbin;
+    if (ok) {
       long long gbin = 0;
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) if (k < K) gbin = gbin * p.nb[k] + j[k];
-      if constexpr (W == 0) atomicAdd(reinterpret_cast<unsigned long long*>(out_row) + gbin, 1ull);
-      else atomicAdd(reinterpret_cast<double*>(out_row) + gbin, wv);
+      global_add(out_row, gbin, wv);
+    }
+    return -1;
+  };
+  // shared adds of up to 4 samples.  Counts: native ATOMS.ADD.  Weighted: atomicAdd(double) on shared
+  // memory, which ptxas expands to LDS + DADD + ATOMS.CAST.SPIN.64 (an explicit atomicCAS loop
+  // compiles to plain ATOMS.CAS.64 and measured >4x slower on B200, so the builtin is used).
+  auto shared_add4 = [&](const int (&wb)[4], const WT (&wv)[4]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (wb[e] >= 0) {
+        if constexpr (W == 0) atomicAdd(reinterpret_cast<unsigned int*>(shist) + wb[e], 1u);
+        else atomicAdd(reinterpret_cast<double*>(shist) + wb[e], static_cast<double>(wv[e]));
+      }
     }
   };
 
@@ -182,15 +215,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       T x[KMAX];
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) x[k] = (k < K) ? px[k][i] : T(0);
-      double wv = 1.0;
-      if (W != 0) wv = static_cast<double>(pw[i]);
-      sample(x, wv, out_row);
+      WT wv[4] = {WT(1), WT(1), WT(1), WT(1)};
+      if constexpr (W != 0) wv[0] = pw[i];
+      int wb[4] = {general_sample(x, static_cast<double>(wv[0]), out_row), -1, -1, -1};
+      shared_add4(wb, wv);
     };
     for (long long i = tid; i < head; i += nthr) scalar_at(i);
     for (long long i = tail0 + tid; i < len; i += nthr) scalar_at(i);
 
     if constexpr (KT != 0) {
-      // vector body: 4 samples per thread per step, two steps in flight for small records
+      // vector body: 4 samples per 16-byte load, U loads in flight per array and thread
       constexpr int U = (sizeof(T) * KMAX + (W == 0 ? 0 : sizeof(WT)) <= 12) ? 2 : 1;
       for (long long g = tid; g < nvec; g += static_cast<long long>(U) * nthr) {
         T xv[U][KMAX][4];
@@ -201,22 +235,78 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
           if (gu < nvec) {
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) load4(px[k] + head, gu, xv[u][k]);
-            if (W != 0) load4(pw + head, gu, wv[u]);
+            if constexpr (W != 0) load4(pw + head, gu, wv[u]);
           }
+          if constexpr (W == 0) { wv[u][0] = wv[u][1] = wv[u][2] = wv[u][3] = WT(1); }
         }
+        int wb[U][4];
+        if constexpr (FAST) {
+          // phase A (branch-free, U*4*K independent chains): guess, certainty, window test
+          unsigned side = 0;   // bit (4u+e) set: that sample needs the side path
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const long long gu = g + static_cast<long long>(u) * nthr;
-          if (gu < nvec) {
+          for (int u = 0; u < U; ++u) {
+            const bool live = g + static_cast<long long>(u) * nthr < nvec;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              bool good = true; int wbin = 0;
+#pragma unroll
+              for (int k = 0; k < KMAX; ++k) {
+                int j;
+                const bool certain = uniform_guess<T>(p, k, xv[u][k][e], j);
+                const unsigned jw = static_cast<unsigned>(j - wlo[k]);
+                good = good & certain & (jw < static_cast<unsigned>(wlen[k]));
+                wbin = wbin * wlen[k] + static_cast<int>(jw);
+              }
+              wb[u][e] = (good & live) ? wbin : -1;
+              side |= (!good & live) ? (1u << (4 * u + e)) : 0u;
+            }
+          }
+          // side path, one sample per trip (a lane rarely has more than one): certain and in range but
+          // outside the window -> global RED; everything else (uncertain, out of range, NaN) -> exact path
+          while (side) {
+            const int idx = __ffs(side) - 1;
+            side &= side - 1;
+            T x[KMAX]; WT wsel = WT(1);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (idx == 4 * u + e) {
+#pragma unroll
+                  for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
+                  wsel = wv[u][e];
+                }
+            bool sure = true; long long gbin = 0;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              int jx; const bool certain = uniform_guess<T>(p, k, x[k], jx);
+              sure = sure & certain & (static_cast<unsigned>(jx) < static_cast<unsigned>(p.nb[k]));
+              gbin = gbin * p.nb[k] + jx;
+            }
+            if (sure) global_add(out_row, gbin, static_cast<double>(wsel));
+            else {
+              const int wbin = general_sample(x, static_cast<double>(wsel), out_row);
+              if (wbin >= 0) {
+                if constexpr (W == 0) atomicAdd(reinterpret_cast<unsigned int*>(shist) + wbin, 1u);
+                else atomicAdd(reinterpret_cast<double*>(shist) + wbin, static_cast<double>(wsel));
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool live = g + static_cast<long long>(u) * nthr < nvec;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               T x[KMAX];
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
-              sample(x, (W != 0) ? static_cast<double>(wv[u][e]) : 1.0, out_row);
+              wb[u][e] = live ? general_sample(x, static_cast<double>(wv[u][e]), out_row) : -1;
             }
           }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) shared_add4(wb[u], wv[u]);
       }
     }
     s += len;
@@ -253,16 +343,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 
 // ---------------------------------------------------------------------------------------------
 // window selection (XHK_WINDOW): marginal histograms of a strided probe of the block, then the
-// densest hyper-rectangle of at most `budget` bins (threshold search + greedy growth).
-// One CTA; its cost (~tens of microseconds) is paid only when the bin space exceeds shared memory.
+// densest hyper-rectangle of at most `budget` bins: starting from the full bin space, repeatedly
+// drop the end slice that loses the least probe mass per freed bin.  One CTA, ~20 us; paid only
+// when the bin space exceeds shared memory, and once per call (the blocks of a call share it).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant__ XhkParams p, XhkWindow* wout, int budget,
                                                            int n_probe) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ int s_first[XHK_MAX_VARS], s_last[XHK_MAX_VARS], s_moff[XHK_MAX_VARS + 1];
-  __shared__ unsigned long long s_lo, s_hi;
-  __shared__ int s_fits;
+  __shared__ int s_moff[XHK_MAX_VARS + 1];
   const int K = p.n_vars, tid = threadIdx.x, nthr = blockDim.x;
   T* sedges = reinterpret_cast<T*>(smem);
   unsigned int* marg = reinterpret_cast<unsigned int*>(smem + ((static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15)));
@@ -274,86 +363,46 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant
   __syncthreads();
   const long long total = p.M * p.N;
   const long long step = total / n_probe > 0 ? total / n_probe : 1;
-  for (long long i = tid; i < n_probe; i += nthr) {
-    const long long pos = i * step;
-    if (pos >= total) break;
-    const long long r = pos / p.N, c = pos - r * p.N;
-    int j[XHK_MAX_VARS]; bool ok = true;
-    for (int k = 0; k < K; ++k) {
-      const T x = (static_cast<const T*>(p.data[k]) + r * p.stride[k])[c];
-      j[k] = classify<T>(p, k, sedges, x);
-      ok = ok && j[k] >= 0;
+  constexpr int PB = 8;  // probe loads in flight per thread
+  for (long long i0 = tid; i0 < n_probe; i0 += static_cast<long long>(PB) * nthr) {
+    T xs[PB][XHK_MAX_VARS];
+#pragma unroll
+    for (int b = 0; b < PB; ++b) {
+      const long long pos = (i0 + static_cast<long long>(b) * nthr) * step;
+      if (i0 + static_cast<long long>(b) * nthr < n_probe && pos < total) {
+        const long long r = pos / p.N, c = pos - r * p.N;
+        for (int k = 0; k < K; ++k) xs[b][k] = (static_cast<const T*>(p.data[k]) + r * p.stride[k])[c];
+      }
     }
-    if (ok) for (int k = 0; k < K; ++k) atomicAdd(&marg[s_moff[k] + j[k]], 1u);
-  }
-  __syncthreads();
-  // density of slice s of variable k: marg * nb[k]  (equal for all slices of a uniform distribution)
-  auto volume_at = [&](unsigned long long th) -> long long {
-    if (tid < XHK_MAX_VARS) { s_first[tid] = 0x7fffffff; s_last[tid] = -1; }
-    __syncthreads();
-    for (int k = 0; k < K; ++k)
-      for (int s = tid; s < p.nb[k]; s += nthr)
-        if (static_cast<unsigned long long>(marg[s_moff[k] + s]) * p.nb[k] >= th) { atomicMin(&s_first[k], s); atomicMax(&s_last[k], s); }
-    __syncthreads();
-    long long vol = 1;
-    for (int k = 0; k < K; ++k) { int l = s_last[k] - s_first[k] + 1; if (s_last[k] < 0) l = 1; vol *= l; if (vol > (1ll << 40)) vol = 1ll << 40; }
-    __syncthreads();
-    return vol;
-  };
-  if (tid == 0) {
-    unsigned long long mx = 0;
-    for (int k = 0; k < K; ++k) for (int s = 0; s < p.nb[k]; ++s) { unsigned long long d = static_cast<unsigned long long>(marg[s_moff[k] + s]) * p.nb[k]; if (d > mx) mx = d; }
-    s_lo = 0; s_hi = mx + 1;
-  }
-  __syncthreads();
-  {
-    const long long v0 = volume_at(1);  // every slice that saw at least one probe sample
-    if (tid == 0) s_fits = (v0 <= budget);
-    __syncthreads();
-  }
-  if (!s_fits) {
-    while (true) {
-      const unsigned long long lo = s_lo, hi = s_hi;
-      if (hi - lo <= 1) break;
-      const unsigned long long mid = lo + (hi - lo) / 2;
-      const long long v = volume_at(mid);
-      if (tid == 0) { if (v <= budget) s_hi = mid; else s_lo = mid; }
-      __syncthreads();
+#pragma unroll
+    for (int b = 0; b < PB; ++b) {
+      const long long pos = (i0 + static_cast<long long>(b) * nthr) * step;
+      if (i0 + static_cast<long long>(b) * nthr < n_probe && pos < total) {
+        int j[XHK_MAX_VARS]; bool ok = true;
+        for (int k = 0; k < K; ++k) { j[k] = exact_bin_inline<T>(p, k, sedges, xs[b][k]); ok = ok && j[k] >= 0; }
+        if (ok) for (int k = 0; k < K; ++k) atomicAdd(&marg[s_moff[k] + j[k]], 1u);
+      }
     }
   }
-  // the box of the final threshold is recomputed serially (sum of nb entries: trivial)
+  __syncthreads();
   if (tid == 0) {
-    const unsigned long long th = s_fits ? 1ull : s_hi;
     int lo[XHK_MAX_VARS], len[XHK_MAX_VARS];
     long long vol = 1;
-    for (int k = 0; k < K; ++k) {
-      int first = -1, last = -1, arg = 0; unsigned int best = 0;
-      for (int s = 0; s < p.nb[k]; ++s) {
-        const unsigned int m = marg[s_moff[k] + s];
-        if (static_cast<unsigned long long>(m) * p.nb[k] >= th) { if (first < 0) first = s; last = s; }
-        if (m > best) { best = m; arg = s; }
-      }
-      if (first < 0) { first = last = arg; }
-      lo[k] = first; len[k] = last - first + 1; vol *= len[k];
-    }
-    // shrink if a degenerate threshold left the box above budget (cannot happen for th = s_hi, kept for safety)
+    for (int k = 0; k < K; ++k) { lo[k] = 0; len[k] = p.nb[k]; vol *= len[k]; }
     while (vol > budget) {
-      int kb = 0; for (int k = 1; k < K; ++k) if (len[k] > len[kb]) kb = k;
-      vol = vol / len[kb] * (len[kb] - 1); len[kb] -= 1;
-    }
-    // greedy growth: add the neighbouring slice with the largest probe mass per added bin while it fits
-    while (true) {
-      int bk = -1, bside = 0; double bgain = -1.0;
+      int bk = -1, bside = 0; unsigned long long bcost = ~0ull;
       for (int k = 0; k < K; ++k) {
-        const long long nv = vol / len[k] * (len[k] + 1);
-        if (nv > budget) continue;
-        if (lo[k] > 0) { double g = (static_cast<double>(marg[s_moff[k] + lo[k] - 1]) + 1e-3) * len[k]; if (g > bgain) { bgain = g; bk = k; bside = -1; } }
-        if (lo[k] + len[k] < p.nb[k]) { double g = (static_cast<double>(marg[s_moff[k] + lo[k] + len[k]]) + 1e-3) * len[k]; if (g > bgain) { bgain = g; bk = k; bside = 1; } }
+        if (len[k] <= 1) continue;
+        const unsigned long long cl = static_cast<unsigned long long>(marg[s_moff[k] + lo[k]]) * len[k];
+        const unsigned long long ch = static_cast<unsigned long long>(marg[s_moff[k] + lo[k] + len[k] - 1]) * len[k];
+        if (cl < bcost) { bcost = cl; bk = k; bside = -1; }
+        if (ch < bcost) { bcost = ch; bk = k; bside = 1; }
       }
       if (bk < 0) break;
-      vol = vol / len[bk] * (len[bk] + 1);
-      if (bside < 0) lo[bk] -= 1;
-      len[bk] += 1;
+      if (bside < 0) lo[bk] += 1;
+      len[bk] -= 1;
+      vol = 1;
+      for (int k = 0; k < K; ++k) vol *= len[k];
     }
     for (int k = 0; k < XHK_MAX_VARS; ++k) { wout->lo[k] = k < K ? lo[k] : 0; wout->len[k] = k < K ? len[k] : 0; }
   }
@@ -439,25 +488,25 @@ __global__ void k_flush(uint4* buf, size_t n16) {
 typedef void (*HistKernel)(const XhkParams);
 
 template <typename T, int W>
-HistKernel pick_k(int K) {
+HistKernel pick_k(int K, bool fast) {
   switch (K) {
-    case 1: return k_hist<T, W, 1>;
-    case 2: return k_hist<T, W, 2>;
-    case 3: return k_hist<T, W, 3>;
-    case 4: return k_hist<T, W, 4>;
-    default: return k_hist<T, W, 0>;
+    case 1: return fast ? k_hist<T, W, 1, true> : k_hist<T, W, 1, false>;
+    case 2: return fast ? k_hist<T, W, 2, true> : k_hist<T, W, 2, false>;
+    case 3: return fast ? k_hist<T, W, 3, true> : k_hist<T, W, 3, false>;
+    case 4: return fast ? k_hist<T, W, 4, true> : k_hist<T, W, 4, false>;
+    default: return k_hist<T, W, 0, false>;
   }
 }
 
-HistKernel pick(int dtype, int w_dtype, int K) {
+HistKernel pick(int dtype, int w_dtype, int K, bool fast) {
   if (dtype == 1) {
-    if (w_dtype == 0) return pick_k<float, 0>(K);
-    if (w_dtype == 1) return pick_k<float, 1>(K);
-    return pick_k<float, 2>(K);
+    if (w_dtype == 0) return pick_k<float, 0>(K, fast);
+    if (w_dtype == 1) return pick_k<float, 1>(K, fast);
+    return pick_k<float, 2>(K, fast);
   }
-  if (w_dtype == 0) return pick_k<double, 0>(K);
-  if (w_dtype == 1) return pick_k<double, 1>(K);
-  return pick_k<double, 2>(K);
+  if (w_dtype == 0) return pick_k<double, 0>(K, fast);
+  if (w_dtype == 1) return pick_k<double, 1>(K, fast);
+  return pick_k<double, 2>(K, fast);
 }
 
 }  // namespace
@@ -465,10 +514,11 @@ HistKernel pick(int dtype, int w_dtype, int K) {
 cudaError_t xhk_set_smem_limits(int max_optin) {
   for (int dt = 1; dt <= 2; ++dt)
     for (int w = 0; w <= 2; ++w)
-      for (int k = 1; k <= 5; ++k) {
-        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick(dt, w, k)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
-        if (e != cudaSuccess) return e;
-      }
+      for (int k = 1; k <= 5; ++k)
+        for (int f = 0; f <= 1; ++f) {
+          cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick(dt, w, k, f != 0)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+          if (e != cudaSuccess) return e;
+        }
   // k_window has a little more static shared memory than k_hist
   cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k_window<float>), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 192);
   if (e != cudaSuccess) return e;
@@ -476,7 +526,7 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
 }
 
 cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l) {
-  HistKernel k = pick(l.dtype, l.w_dtype, p.n_vars);
+  HistKernel k = pick(l.dtype, l.w_dtype, p.n_vars, p.all_uniform != 0);
   k<<<l.grid, l.threads, l.smem_bytes, l.stream>>>(p);
   return cudaGetLastError();
 }

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #define XHK_MAX_VARS 8
+enum { XHK_C_LO = 0, XHK_C_HI = 1, XHK_C_E0 = 2, XHK_C_INV = 3, XHK_C_DELTA = 4, XHK_C_OMD = 5 };
 
 // How the per-CTA shared-memory histogram is used.
 enum XhkHistMode {
@@ -32,15 +33,15 @@ struct XhkParams {
   long long stride[XHK_MAX_VARS];   // row stride in elements (0 = broadcast row)
   const void* w;
   long long wstride;
-  // classification constants, typed T (float or double) in the first sizeof(T) bytes of each slot
-  double lo[XHK_MAX_VARS];          // smallest in-range value  (effective first edge)
-  double hi[XHK_MAX_VARS];          // largest in-range value   (effective last edge)
-  double e0[XHK_MAX_VARS];          // uniform path: t = (x - e0) * inv
-  double inv[XHK_MAX_VARS];
-  double delta[XHK_MAX_VARS];       // uniform path: bin certain iff delta <= frac(t) <= omd
-  double omd[XHK_MAX_VARS];
+  // classification constants per variable, typed: cf for fp32 kernels, cd for fp64 kernels.
+  //   [XHK_C_LO] smallest in-range value (effective first edge)   [XHK_C_HI] largest in-range value
+  //   [XHK_C_E0],[XHK_C_INV] uniform path t = (x - e0) * inv
+  //   [XHK_C_DELTA],[XHK_C_OMD] uniform path: bin certain iff delta <= frac(t) <= omd
+  float cf[XHK_MAX_VARS][6];
+  double cd[XHK_MAX_VARS][6];
   int nb[XHK_MAX_VARS];             // bins of variable k  (= n_edges - 1)
   int uniform[XHK_MAX_VARS];        // 1: uniform fast path usable for variable k
+  int all_uniform;                  // 1: every variable is uniform -> branch-free fast classification kernel
   int eoff[XHK_MAX_VARS];           // offset of variable k's effective edges in `edges`
   long long gmul[XHK_MAX_VARS];     // C-order multipliers of the global bin index
   const void* edges;                // device, typed T, all variables concatenated

@@ -164,17 +164,55 @@ def histogram(*local_args, bins=None, range=None, axis=None, weights=None, densi
             edges.append(np.histogram_bin_edges(np.array([mn, mx], dtype=dt), bins=b))
         else:
             edges.append(_core._resolve_edges(a if _core.is_device_array(a) else np.asarray(a), b, r, None))
-    h, _ = _core.histogram(*local_args, bins=edges, axis=axis, weights=weights, density=False, block_size=block_size)
     if sharded_axis in red:
-        h = comm.allreduce_sum(np.ascontiguousarray(h))             # partial histograms -> global (core.py:439)
-    elif gather:
-        kept = [i for i in _range(nd) if i not in red]
-        pos = kept.index(sharded_axis)
-        hm = np.ascontiguousarray(np.moveaxis(h, pos, 0))
-        counts = comm.allreduce_sum(np.eye(comm.world, dtype=np.int64)[comm.rank] * hm.shape[0])
-        h = np.moveaxis(comm.allgather_rows(hm, counts), 0, pos)
+        if isinstance(comm, NcclCommunicator) and _core.is_device_array(a0):
+            h = _device_partial_allreduce(local_args, weights, edges, axis, nd, comm)   # partial stays in HBM
+        else:
+            h, _ = _core.histogram(*local_args, bins=edges, axis=axis, weights=weights, density=False, block_size=block_size)
+            h = comm.allreduce_sum(np.ascontiguousarray(h))         # partial histograms -> global (core.py:439)
+    else:
+        h, _ = _core.histogram(*local_args, bins=edges, axis=axis, weights=weights, density=False, block_size=block_size)
+        if gather:
+            kept = [i for i in _range(nd) if i not in red]
+            pos = kept.index(sharded_axis)
+            hm = np.ascontiguousarray(np.moveaxis(h, pos, 0))
+            counts = comm.allreduce_sum(np.eye(comm.world, dtype=np.int64)[comm.rank] * hm.shape[0])
+            h = np.moveaxis(comm.allgather_rows(hm, counts), 0, pos)
     if density:                                                     # after the reduce, on O(bins) data (core.py:444-462)
         areas = functools.reduce(np.multiply.outer, [np.diff(e) for e in edges])
         bin_axes = tuple(_range(-n, 0))
         h = h / areas / h.sum(axis=bin_axes, keepdims=True)
     return h, edges
+
+
+def _device_partial_allreduce(local_args, weights, edges, axis, nd, comm):
+    """Device-resident shard -> partial histogram in HBM -> ncclAllReduce in place -> one D2H of the result."""
+    from .device import DeviceArray
+
+    shape = _core.as_device_view(local_args[0])[1]
+    ax = None if axis is None else [int(a) if a >= 0 else nd + int(a) for a in np.atleast_1d(axis)]
+    full = ax is None or set(ax) == set(_range(nd))
+    kept_shape = () if full else tuple(shape[i] for i in _range(nd) if i not in ax)
+    nbins = tuple(len(e) - 1 for e in edges)
+    M = int(np.prod(kept_shape, dtype=np.int64)) if kept_shape else 1
+    B = int(np.prod(nbins, dtype=np.int64))
+    out = _partial_buffer(comm.device, M * B)
+    arrays = list(local_args) + ([weights] if weights is not None else [])
+    _core._bincount(*arrays, weights=weights is not None, axis=ax, bins=edges, _out_device=out)
+    comm.allreduce_device(out.ptr, M * B, weights is not None)
+    h = out.to_numpy()
+    h = h if weights is not None else h.view(np.int64)
+    return h.reshape(kept_shape + nbins)
+
+
+_partials = {}
+
+
+def _partial_buffer(device, n):
+    from .device import DeviceArray
+
+    buf = _partials.get(device)
+    if buf is None or buf.size < n:
+        buf = DeviceArray((n,), np.float64, device)
+        _partials[device] = buf
+    return buf if buf.size == n else buf.flat_slice(0, n)

@@ -230,7 +230,7 @@ int prep_call(const xh_desc* d, Prep& pr) {
     B *= p.nb[k];
   }
   p.B = B;
-  p.all_uniform = 1;
+  p.all_uniform = (B < 2147483646ll) ? 1 : 0;     // the fast kernel encodes global bins in an int
   for (int k = 0; k < K; ++k) p.all_uniform = p.all_uniform && p.uniform[k];
   long long mul = 1;
   for (int k = K - 1; k >= 0; --k) { p.gmul[k] = mul; mul *= p.nb[k]; }
@@ -282,12 +282,12 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
   if (mode == XHK_WINDOW && (static_cast<long long>(edges_al) + marg_bytes > c->smem_optin - 256 || cap1 < 1)) mode = XHK_GLOBAL;
   p.hist_mode = mode;
 
-  int ctas_per_sm = 1, threads = 1024;
+  int ctas_per_sm = 1, threads = XHK_THREADS;   // k_hist is compiled for <= XHK_THREADS threads per CTA
   size_t smem = edges_al;
   if (mode == XHK_FULL) {
     smem = edges_al + static_cast<size_t>(B) * item;
     // two 512-thread CTAs per SM when both histograms fit (a flush of one overlaps the stream of the other)
-    if (2 * (smem + 1024 + 64) <= static_cast<size_t>(c->smem_per_sm)) { ctas_per_sm = 2; threads = 512; }
+    if (2 * (smem + 1024 + 64) <= static_cast<size_t>(c->smem_per_sm)) { ctas_per_sm = 2; threads = XHK_THREADS / 2; }
     p.hist_capacity = static_cast<int>(B);
   } else if (mode == XHK_WINDOW) {
     long long cap = cap1;
@@ -296,7 +296,7 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
     smem = edges_al + static_cast<size_t>(pl.window_budget) * item;
     p.hist_capacity = pl.window_budget;
   } else {
-    ctas_per_sm = 2; threads = 512;
+    ctas_per_sm = 2; threads = XHK_THREADS / 2;
   }
   const long long total = p.M * p.N;
   int grid = c->sm_count * ctas_per_sm;
@@ -309,6 +309,18 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
     per = (per + 1023) / 1024 * 1024;
     p.per_cta = per;
     grid = static_cast<int>((total + per - 1) / per);
+  }
+  // fixed-point headroom: at most A adds reach one bin between two flushes of a CTA
+  {
+    long long A = std::min<long long>(p.N, 1ll << 30);
+    if (p.partition == XHK_PART_SAMPLES) A = std::min<long long>(A, p.per_cta);
+    int lg = 0; while ((1ll << lg) < A) ++lg;
+    p.fx_vbits = std::max(24, std::min(50, 62 - lg));
+    p.w_dtype = d->w_dtype;
+    if (d->w_dtype != XH_NONE && mode != XHK_GLOBAL && !pl.need_window) {
+      pl.need_window = true;                                   // FULL mode still needs the weight probe
+      pl.window_budget = static_cast<int>(std::min<long long>(B, 1ll << 30));
+    }
   }
   const bool no_zero = (d->flags & XH_FLAG_NO_ZERO) != 0;
   p.store_owned_rows = (mode == XHK_FULL && !no_zero && !(p.M > 1 && p.N > (1ll << 30))) ? 1 : 0;

@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int kMaxThreads = 1024;
+constexpr int kMaxThreads = XHK_THREADS;
 constexpr long long kSegCap = 1ll << 30;  // u32 shared counters are flushed at least this often
 
 template <typename T> struct Consts;
@@ -30,6 +30,21 @@ template <> struct Consts<double> {
 
 __device__ __forceinline__ int floor_to_int(float t) { return __float2int_rd(t); }
 __device__ __forceinline__ int floor_to_int(double t) { return __double2int_rd(t); }
+
+// shared-memory atomics on explicit 32-bit shared addresses (no generic->shared conversion per use)
+__device__ __forceinline__ void reds_add_u32(unsigned addr, unsigned v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned atoms_add_u32(unsigned addr, unsigned v) {
+  unsigned old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_add_f64(unsigned addr, double v) {
+  asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ long long to_ll_rn(float v) { return __float2ll_rn(v); }
+__device__ __forceinline__ long long to_ll_rn(double v) { return __double2ll_rn(v); }
 
 // ---------------------------------------------------------------------------------------------
 // classification: bin of x for variable k, or -1 when x is dropped.
@@ -132,6 +147,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
     if (k < K) { wlo[k] = s_wlo[k]; wlen[k] = s_wlen[k]; wtot *= wlen[k]; } else { wlo[k] = 0; wlen[k] = 0; }
   }
   for (int i = tid; i < wtot; i += nthr) shist[i] = HT(0);
+  // weighted accumulation mode (uniform for the launch): exact fixed point in two u32 limbs, or float64 adds
+  bool fx = false; WT fx_mul = WT(0), fx_limit = WT(0); double fx_unmul = 0.0;
+  if constexpr (W != 0) {
+    if (p.hist_mode != XHK_GLOBAL && p.window->fx_ok) {
+      fx = true; fx_mul = static_cast<WT>(p.window->fx_mul); fx_limit = static_cast<WT>(p.window->fx_limit); fx_unmul = p.window->fx_unmul;
+    }
+  }
+  const unsigned sh_lo = static_cast<unsigned>(__cvta_generic_to_shared(shist));   // counts / lo limbs / doubles
+  const unsigned sh_hi = sh_lo + 4u * static_cast<unsigned>(wtot);                  // hi limbs (fixed point)
   __syncthreads();
 
   OT* const out = static_cast<OT*>(p.out);
@@ -172,17 +196,47 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
     }
     return -1;
   };
-  // shared adds of up to 4 samples.  Counts: native ATOMS.ADD.  Weighted: atomicAdd(double) on shared
-  // memory, which ptxas expands to LDS + DADD + ATOMS.CAST.SPIN.64 (an explicit atomicCAS loop
-  // compiles to plain ATOMS.CAS.64 and measured >4x slower on B200, so the builtin is used).
-  auto shared_add4 = [&](const int (&wb)[4], const WT (&wv)[4]) {
+  // window bin -> global bin (rare paths only)
+  auto window_to_global = [&](int wbin) -> long long {
+    int rem = wbin; long long gbin = 0;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (wb[e] >= 0) {
-        if constexpr (W == 0) atomicAdd(reinterpret_cast<unsigned int*>(shist) + wb[e], 1u);
-        else atomicAdd(reinterpret_cast<double*>(shist) + wb[e], static_cast<double>(wv[e]));
+    for (int k = KMAX - 1; k >= 0; --k) {
+      if (k < K) { const int q = rem / wlen[k]; const int c = rem - q * wlen[k]; rem = q; gbin += (wlo[k] + c) * p.gmul[k]; }
+    }
+    return gbin;
+  };
+  // shared add of one sample.
+  //  counts   : native RED.ADD.U32.
+  //  weighted : fixed point (fx) — v = w * 2^-s as a 64-bit integer split over two u32 limbs: one native
+  //             ATOMS.ADD on the low limb (its return value gives the carry) and a RED on the high limb when
+  //             it is non-zero.  Integer adds are exact and order independent; a weight that is not an exact
+  //             multiple of 2^s below the limit (also NaN/inf) goes to a float64 global RED instead.
+  //             Otherwise float64 adds in shared memory (red.shared.add.f64 = LDS + DADD + ATOMS.CAST.SPIN loop;
+  //             an explicit atomicCAS loop compiles to plain ATOMS.CAS.64 and measured >4x slower on B200).
+  auto shared_add1 = [&](int wbin, WT w, OT* out_row) {
+    if constexpr (W == 0) {
+      reds_add_u32(sh_lo + 4u * static_cast<unsigned>(wbin), 1u);
+    } else {
+      if (fx) {
+        const WT vs = w * fx_mul;
+        const long long v = to_ll_rn(vs);
+        if ((static_cast<WT>(v) == vs) & (fabs(vs) < fx_limit)) {
+          const unsigned lo = static_cast<unsigned>(v);
+          unsigned hi = static_cast<unsigned>(static_cast<unsigned long long>(v) >> 32);
+          const unsigned old = atoms_add_u32(sh_lo + 4u * static_cast<unsigned>(wbin), lo);
+          hi += (old + lo < old) ? 1u : 0u;
+          if (hi) reds_add_u32(sh_hi + 4u * static_cast<unsigned>(wbin), hi);
+        } else {
+          atomicAdd(out_row + window_to_global(wbin), static_cast<double>(w));
+        }
+      } else {
+        reds_add_f64(sh_lo + 8u * static_cast<unsigned>(wbin), static_cast<double>(w));
       }
     }
+  };
+  auto shared_add4 = [&](const int (&wb)[4], const WT (&wv)[4], OT* out_row) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) if (wb[e] >= 0) shared_add1(wb[e], wv[e], out_row);
   };
 
   long long s = s0;
@@ -217,8 +271,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       for (int k = 0; k < KMAX; ++k) x[k] = (k < K) ? px[k][i] : T(0);
       WT wv[4] = {WT(1), WT(1), WT(1), WT(1)};
       if constexpr (W != 0) wv[0] = pw[i];
-      int wb[4] = {general_sample(x, static_cast<double>(wv[0]), out_row), -1, -1, -1};
-      shared_add4(wb, wv);
+      const int wbin = general_sample(x, static_cast<double>(wv[0]), out_row);
+      if (wbin >= 0) shared_add1(wbin, wv[0], out_row);
     };
     for (long long i = tid; i < head; i += nthr) scalar_at(i);
     for (long long i = tail0 + tid; i < len; i += nthr) scalar_at(i);
@@ -286,10 +340,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             if (sure) global_add(out_row, gbin, static_cast<double>(wsel));
             else {
               const int wbin = general_sample(x, static_cast<double>(wsel), out_row);
-              if (wbin >= 0) {
-                if constexpr (W == 0) atomicAdd(reinterpret_cast<unsigned int*>(shist) + wbin, 1u);
-                else atomicAdd(reinterpret_cast<double*>(shist) + wbin, static_cast<double>(wsel));
-              }
+              if (wbin >= 0) shared_add1(wbin, wsel, out_row);
             }
           }
         } else {
@@ -306,35 +357,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
           }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) shared_add4(wb[u], wv[u]);
+        for (int u = 0; u < U; ++u) shared_add4(wb[u], wv[u], out_row);
       }
     }
     s += len;
 
     // ---- flush the shared histogram of this row segment and clear it
     __syncthreads();
-    if (p.hist_mode == XHK_FULL) {
-      const bool owned = p.store_owned_rows && c0 == 0 && len == p.N;
-      if (owned) {
-        for (int b = tid; b < wtot; b += nthr) { out_row[b] = static_cast<OT>(shist[b]); shist[b] = HT(0); }
-      } else {
-        for (int b = tid; b < wtot; b += nthr) {
-          const HT v = shist[b];
-          if (v != HT(0)) { atomicAdd(out_row + b, static_cast<OT>(v)); shist[b] = HT(0); }
-        }
-      }
-    } else if (p.hist_mode == XHK_WINDOW) {
+    if (p.hist_mode != XHK_GLOBAL) {
+      const bool full = p.hist_mode == XHK_FULL;
+      const bool owned = full && p.store_owned_rows && c0 == 0 && len == p.N;
+      unsigned int* lo32 = reinterpret_cast<unsigned int*>(shist);
+      unsigned int* hi32 = lo32 + wtot;
       for (int b = tid; b < wtot; b += nthr) {
-        const HT v = shist[b];
-        if (v != HT(0)) {
-          int rem = b; long long gbin = 0;
-#pragma unroll
-          for (int k = KMAX - 1; k >= 0; --k) {
-            if (k < K) { const int q = rem / wlen[k]; const int c = rem - q * wlen[k]; rem = q; gbin += (wlo[k] + c) * p.gmul[k]; }
-          }
-          atomicAdd(out_row + gbin, static_cast<OT>(v));
-          shist[b] = HT(0);
-        }
+        OT v; bool nz;
+        if constexpr (W == 0) { v = static_cast<OT>(shist[b]); nz = v != 0; shist[b] = 0u; }
+        else if (fx) {
+          const long long iv = static_cast<long long>((static_cast<unsigned long long>(hi32[b]) << 32) | lo32[b]);
+          nz = iv != 0; v = static_cast<double>(iv) * fx_unmul;
+          lo32[b] = 0u; hi32[b] = 0u;
+        } else { v = shist[b]; nz = v != 0.0; shist[b] = 0.0; }
+        if (owned) out_row[b] = v;
+        else if (nz) atomicAdd(out_row + (full ? static_cast<long long>(b) : window_to_global(b)), v);
       }
     }
     __syncthreads();
@@ -342,69 +386,157 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------
-// window selection (XHK_WINDOW): marginal histograms of a strided probe of the block, then the
-// densest hyper-rectangle of at most `budget` bins: starting from the full bin space, repeatedly
-// drop the end slice that loses the least probe mass per freed bin.  One CTA, ~20 us; paid only
-// when the bin space exceeds shared memory, and once per call (the blocks of a call share it).
+// probe kernel: (1) marginal histograms of a strided probe of the block -> the densest hyper-rectangle
+// of at most `budget` bins (XHK_WINDOW); (2) the fixed-point scale of the weights.  One CTA, ~10-20 us;
+// run once per call when the bin space exceeds shared memory or weights are present.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant__ XhkParams p, XhkWindow* wout, int budget,
                                                            int n_probe) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_moff[XHK_MAX_VARS + 1];
+  __shared__ unsigned long long s_wmax;
+  __shared__ int s_fail, s_seen;
+  __shared__ double s_mul, s_limit;
   const int K = p.n_vars, tid = threadIdx.x, nthr = blockDim.x;
   T* sedges = reinterpret_cast<T*>(smem);
   unsigned int* marg = reinterpret_cast<unsigned int*>(smem + ((static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15)));
   for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
-  if (tid == 0) { int o = 0; for (int k = 0; k < K; ++k) { s_moff[k] = o; o += p.nb[k]; } s_moff[K] = o; }
+  if (tid == 0) { int o = 0; for (int k = 0; k < K; ++k) { s_moff[k] = o; o += p.nb[k]; } s_moff[K] = o; s_wmax = 0ull; s_fail = 0; s_seen = 0; }
   __syncthreads();
   const int mtot = s_moff[K];
   for (int i = tid; i < mtot; i += nthr) marg[i] = 0u;
   __syncthreads();
   const long long total = p.M * p.N;
   const long long step = total / n_probe > 0 ? total / n_probe : 1;
-  constexpr int PB = 8;  // probe loads in flight per thread
+  const bool flat = p.M == 1;
+  auto locate = [&](long long pos, long long& r, long long& c) {
+    if (flat) { r = 0; c = pos; } else { r = pos / p.N; c = pos - r * p.N; }
+  };
+  auto wload = [&](long long r, long long c) -> double {
+    return p.w_dtype == 1 ? static_cast<double>((static_cast<const float*>(p.w) + r * p.wstride)[c])
+                          : (static_cast<const double*>(p.w) + r * p.wstride)[c];
+  };
+  constexpr int PB = 8;  // probe positions in flight per thread
+  unsigned long long wmx = 0ull;
+  double wkeep[2 * PB]; int nkeep = 0;   // this thread's probe weights (n_probe <= 2*PB*blockDim)
   for (long long i0 = tid; i0 < n_probe; i0 += static_cast<long long>(PB) * nthr) {
-    T xs[PB][XHK_MAX_VARS];
+    T xs[PB][XHK_MAX_VARS]; double ws[PB]; bool have[PB];
 #pragma unroll
     for (int b = 0; b < PB; ++b) {
-      const long long pos = (i0 + static_cast<long long>(b) * nthr) * step;
-      if (i0 + static_cast<long long>(b) * nthr < n_probe && pos < total) {
-        const long long r = pos / p.N, c = pos - r * p.N;
+      const long long i = i0 + static_cast<long long>(b) * nthr;
+      const long long pos = i * step;
+      have[b] = i < n_probe && pos < total;
+      ws[b] = 0.0;
+      if (have[b]) {
+        long long r, c; locate(pos, r, c);
         for (int k = 0; k < K; ++k) xs[b][k] = (static_cast<const T*>(p.data[k]) + r * p.stride[k])[c];
+        if (p.w_dtype != 0) ws[b] = wload(r, c);
       }
     }
 #pragma unroll
     for (int b = 0; b < PB; ++b) {
-      const long long pos = (i0 + static_cast<long long>(b) * nthr) * step;
-      if (i0 + static_cast<long long>(b) * nthr < n_probe && pos < total) {
+      if (have[b]) {
         int j[XHK_MAX_VARS]; bool ok = true;
         for (int k = 0; k < K; ++k) { j[k] = exact_bin_inline<T>(p, k, sedges, xs[b][k]); ok = ok && j[k] >= 0; }
         if (ok) for (int k = 0; k < K; ++k) atomicAdd(&marg[s_moff[k] + j[k]], 1u);
+        if (p.w_dtype != 0) {
+          const double a = fabs(ws[b]);
+          if (a < INFINITY) { const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(a)); if (bits > wmx) wmx = bits; }
+          if (nkeep < 2 * PB) wkeep[nkeep++] = ws[b];
+        }
       }
     }
   }
+  if (p.w_dtype != 0) {   // non-negative doubles order like their bit patterns; one shared atomic per warp
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, wmx, o); if (t > wmx) wmx = t; }
+    if ((tid & 31) == 0) atomicMax(&s_wmax, wmx);
+  }
   __syncthreads();
-  if (tid == 0) {
-    int lo[XHK_MAX_VARS], len[XHK_MAX_VARS];
-    long long vol = 1;
-    for (int k = 0; k < K; ++k) { lo[k] = 0; len[k] = p.nb[k]; vol *= len[k]; }
-    while (vol > budget) {
-      int bk = -1, bside = 0; unsigned long long bcost = ~0ull;
-      for (int k = 0; k < K; ++k) {
-        if (len[k] <= 1) continue;
-        const unsigned long long cl = static_cast<unsigned long long>(marg[s_moff[k] + lo[k]]) * len[k];
-        const unsigned long long ch = static_cast<unsigned long long>(marg[s_moff[k] + lo[k] + len[k] - 1]) * len[k];
-        if (cl < bcost) { bcost = cl; bk = k; bside = -1; }
-        if (ch < bcost) { bcost = ch; bk = k; bside = 1; }
-      }
-      if (bk < 0) break;
-      if (bside < 0) lo[bk] += 1;
-      len[bk] -= 1;
-      vol = 1;
-      for (int k = 0; k < K; ++k) vol *= len[k];
+  // ---- weights: scale from the largest finite probe weight; count the probe weights that would not be
+  //      exact at that scale; too many (> 1/64) -> float64 shared adds instead of fixed point
+  if (p.w_dtype != 0) {
+    if (tid == 0) {
+      const double m = __longlong_as_double(static_cast<long long>(s_wmax));
+      const int e = m > 0.0 ? ilogb(m) : 0;
+      const int sh = p.fx_vbits - 3 - e;          // v = w * 2^sh ; the largest probe weight maps below 2^(vbits-2)
+      s_mul = ldexp(1.0, sh); s_limit = ldexp(1.0, p.fx_vbits);
+      s_seen = (p.w_dtype == 1 && (sh > 100 || sh < -100)) ? -(1 << 30) : 0;   // outside fp32's exact power-of-two range
     }
-    for (int k = 0; k < XHK_MAX_VARS; ++k) { wout->lo[k] = k < K ? lo[k] : 0; wout->len[k] = k < K ? len[k] : 0; }
+    __syncthreads();
+    int fails = 0;
+    for (int i = 0; i < nkeep; ++i) {
+      const double vs = wkeep[i] * s_mul;
+      if (!((static_cast<double>(__double2ll_rn(vs)) == vs) & (fabs(vs) < s_limit))) ++fails;
+    }
+    int seen = nkeep;
+    for (int o = 16; o > 0; o >>= 1) { fails += __shfl_xor_sync(0xffffffffu, fails, o); seen += __shfl_xor_sync(0xffffffffu, seen, o); }
+    if ((tid & 31) == 0 && seen) { atomicAdd(&s_fail, fails); atomicAdd(&s_seen, seen); }
+    __syncthreads();
+    if (tid == 0) {
+      wout->fx_mul = s_mul; wout->fx_unmul = 1.0 / s_mul; wout->fx_limit = s_limit;
+      wout->fx_ok = (s_seen > 0 && static_cast<long long>(s_fail) * 64 <= s_seen) ? 1 : 0;
+    }
+  } else if (tid == 0) { wout->fx_ok = 0; wout->fx_mul = 0.0; wout->fx_unmul = 0.0; wout->fx_limit = 0.0; }
+
+  // ---- window: warp 0 bisects a density threshold (density of slice s of variable k = marg * nb_k, equal for
+  //      all slices of a uniform distribution); the box of variable k spans the slices at or above the
+  //      threshold.  Then lane 0 grows the box greedily while it fits the budget.
+  if (tid < 32) {
+    const unsigned full = 0xffffffffu;
+    auto box_at = [&](unsigned long long th, int* lo, int* len) -> long long {
+      long long vol = 1;
+      for (int k = 0; k < K; ++k) {
+        int first = 0x7fffffff, last = -1;
+        for (int s = tid; s < p.nb[k]; s += 32)
+          if (static_cast<unsigned long long>(marg[s_moff[k] + s]) * p.nb[k] >= th) { first = min(first, s); last = max(last, s); }
+        for (int o = 16; o > 0; o >>= 1) { first = min(first, __shfl_xor_sync(full, first, o)); last = max(last, __shfl_xor_sync(full, last, o)); }
+        if (last < 0) { first = 0; last = 0; }   // fixed up below (arg max)
+        lo[k] = first; len[k] = last - first + 1;
+        vol *= len[k]; if (vol > (1ll << 40)) vol = 1ll << 40;
+      }
+      return vol;
+    };
+    unsigned long long dmax = 0;
+    for (int k = 0; k < K; ++k)
+      for (int s = tid; s < p.nb[k]; s += 32) { const unsigned long long d = static_cast<unsigned long long>(marg[s_moff[k] + s]) * p.nb[k]; if (d > dmax) dmax = d; }
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(full, dmax, o); if (t > dmax) dmax = t; }
+    int lo[XHK_MAX_VARS], len[XHK_MAX_VARS];
+    unsigned long long tlo = 0, thi = dmax + 1;           // vol(tlo) > budget (unless everything fits), vol(thi) <= budget
+    if (box_at(0, lo, len) > budget) {
+      while (thi - tlo > 1) {
+        const unsigned long long mid = tlo + (thi - tlo) / 2;
+        if (box_at(mid, lo, len) <= budget) thi = mid; else tlo = mid;
+      }
+      long long vol = box_at(thi, lo, len);
+      if (tid == 0) {
+        // a variable with no slice at the threshold keeps its fullest slice
+        for (int k = 0; k < K; ++k) {
+          bool any = false;
+          for (int s = lo[k]; s < lo[k] + len[k]; ++s) any = any || static_cast<unsigned long long>(marg[s_moff[k] + s]) * p.nb[k] >= thi;
+          if (!any) { int arg = 0; unsigned best = 0; for (int s = 0; s < p.nb[k]; ++s) if (marg[s_moff[k] + s] > best) { best = marg[s_moff[k] + s]; arg = s; } lo[k] = arg; len[k] = 1; }
+        }
+        vol = 1; for (int k = 0; k < K; ++k) vol *= len[k];
+        while (vol > budget) {   // cannot happen for a consistent threshold; kept as a guard
+          int kb = 0; for (int k = 1; k < K; ++k) if (len[k] > len[kb]) kb = k;
+          len[kb] -= 1; vol = 1; for (int k = 0; k < K; ++k) vol *= len[k];
+        }
+        while (true) {           // greedy growth: neighbouring slice with the most probe mass per added bin
+          int bk = -1, bside = 0; double bgain = -1.0;
+          for (int k = 0; k < K; ++k) {
+            long long nv = 1; for (int q = 0; q < K; ++q) nv *= (q == k ? len[q] + 1 : len[q]);
+            if (nv > budget) continue;
+            if (lo[k] > 0) { const double g = (static_cast<double>(marg[s_moff[k] + lo[k] - 1]) + 1e-3) * len[k]; if (g > bgain) { bgain = g; bk = k; bside = -1; } }
+            if (lo[k] + len[k] < p.nb[k]) { const double g = (static_cast<double>(marg[s_moff[k] + lo[k] + len[k]]) + 1e-3) * len[k]; if (g > bgain) { bgain = g; bk = k; bside = 1; } }
+          }
+          if (bk < 0) break;
+          if (bside < 0) lo[bk] -= 1;
+          len[bk] += 1;
+        }
+      }
+    }
+    if (tid == 0)
+      for (int k = 0; k < XHK_MAX_VARS; ++k) { wout->lo[k] = k < K ? lo[k] : 0; wout->len[k] = k < K ? len[k] : 0; }
   }
 }
 

@@ -5,6 +5,10 @@
 #include <stdint.h>
 
 #define XHK_MAX_VARS 8
+// threads of a k_hist CTA when one CTA owns an SM (register budget: 65536 / XHK_THREADS per thread)
+#ifndef XHK_THREADS
+#define XHK_THREADS 1024
+#endif
 enum { XHK_C_LO = 0, XHK_C_HI = 1, XHK_C_E0 = 2, XHK_C_INV = 3, XHK_C_DELTA = 4, XHK_C_OMD = 5 };
 
 // How the per-CTA shared-memory histogram is used.
@@ -24,6 +28,12 @@ enum XhkPartition {
 struct XhkWindow {
   int lo[XHK_MAX_VARS];
   int len[XHK_MAX_VARS];
+  // exact fixed-point accumulation of the weights (chosen by the probe kernel):
+  // v = w * fx_mul is accumulated as a 64-bit integer in two u32 shared limbs when it is an integer
+  // below fx_limit; anything else goes to a float64 global RED.  fx_ok = 0 -> float64 shared adds instead.
+  double fx_mul, fx_unmul, fx_limit;
+  int fx_ok;
+  int pad;
 };
 
 // Kernel parameters (passed by value, lives in the constant bank).
@@ -58,6 +68,8 @@ struct XhkParams {
   int wlo[XHK_MAX_VARS];            // XHK_FULL: 0 / nb ; ignored otherwise
   int wlen[XHK_MAX_VARS];
   long long per_cta;                // XHK_PART_SAMPLES: samples per CTA (multiple of 1024)
+  int w_dtype;                      // 0 none, 1 fp32, 2 fp64 (for the probe kernel)
+  int fx_vbits;                     // fixed point: |v| < 2^fx_vbits keeps every per-flush bin sum below 2^63
 };
 
 struct XhkLaunch {

@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Device-resident kernel timings of the five BASELINE.json configurations (1 GPU).
+
+Not the driver's bench (that is bench.py, config 3); this reports, for every configuration, the
+kernel time of one call (CUDA events inside the C-ABI), the algorithmic bytes
+(inputs read once + histogram written once) and the fraction of the measured HBM peak.
+Multi-GPU configurations are run as the per-GPU shard of the 8-GPU case.
+
+    python tools/bench_configs.py [--reps 5] [--scale 1.0]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from xhistogram_b200 import DeviceArray, core  # noqa: E402
+
+
+def timed(args, weights, bins, axis, reps):
+    t = {}
+    arrays = list(args) + ([weights] if weights is not None else [])
+    ms = []
+    out = None
+    for _ in range(reps + 2):
+        out = core._bincount(*arrays, weights=weights is not None, axis=axis, bins=bins, _timing=t)
+        ms.append(t["kernel_ms"])
+    return out, float(np.min(ms[2:])), float(np.median(ms[2:]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--scale", type=float, default=1.0, help="scale the sample counts (smoke runs)")
+    a = ap.parse_args()
+    peak = 6546.2
+    pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(pp):
+        peak = float(json.load(open(pp))["hbm_gbs"])
+    sc = a.scale
+    rows = []
+
+    def report(name, samples, nbytes, best, med, note=""):
+        gbs = nbytes / (best * 1e-3) / 1e9
+        rows.append(dict(config=name, samples=samples, algorithmic_bytes=nbytes, kernel_ms_best=best, kernel_ms_median=med,
+                         gsamples_per_s=samples / (best * 1e-3) / 1e9, gb_per_s=gbs, frac_of_measured_hbm=gbs / peak, note=note))
+        print(json.dumps(rows[-1]), flush=True)
+
+    # cfg1: 1-D, 1e6 fp32, 100 uniform bins (bins=int -> device min/max + fp32 edges), launch-latency bound
+    n = int(1e6)
+    x = DeviceArray.uniform((n,), np.float32, seed=0)
+    edges = core._resolve_edges(x, 100, None, None)
+    _, best, med = timed([x], None, [edges], None, a.reps)
+    report("cfg1 1-D 1e6 fp32, 100 bins", n, n * 4 + 100 * 8, best, med, "launch-latency bound; not graded on roofline")
+    x.free()
+
+    # cfg2: 2 x fp32 (1e4, 1e5), 128x128, axis=-1, counts
+    M, N = max(1, int(1e4 * sc)), int(1e5)
+    x = DeviceArray.normal((M, N), np.float32, seed=1); y = DeviceArray.normal((M, N), np.float32, seed=2)
+    e = np.linspace(-4, 4, 129)
+    _, best, med = timed([x, y], None, [e, e], [1], a.reps)
+    report("cfg2 2xfp32 (1e4,1e5) 128x128 axis=-1", M * N, M * N * 8 + M * 128 * 128 * 8, best, med)
+    x.free(); y.free()
+
+    # cfg3: headline (see bench.py)
+    n = int(1e9 * sc)
+    x = DeviceArray.normal((n,), np.float32, seed=3); y = DeviceArray.normal((n,), np.float32, seed=4)
+    w = DeviceArray.uniform((n,), np.float32, seed=5)
+    e = np.linspace(-4, 4, 257)
+    _, best, med = timed([x, y], w, [e, e], None, a.reps)
+    report("cfg3 2xfp32 (1e9,) fp32 w 256x256", n, n * 12 + 256 * 256 * 8, best, med)
+    _, best, med = timed([x, y], None, [e, e], None, a.reps)
+    report("cfg3-counts 2xfp32 (1e9,) 256x256 no weights", n, n * 8 + 256 * 256 * 8, best, med)
+    x.free(); y.free(); w.free()
+
+    # cfg4: per-GPU shard of (8192, 720, 1440): 1024 time steps, 100x100 bins, reduce (lat, lon)
+    M, N = max(1, int(1024 * sc)), 720 * 1440
+    x = DeviceArray.normal((M, 720, 1440), np.float32, seed=6); y = DeviceArray.normal((M, 720, 1440), np.float32, seed=7)
+    e = np.linspace(-4, 4, 101)
+    _, best, med = timed([x, y], None, [e, e], [1, 2], a.reps)
+    report("cfg4 shard 2xfp32 (1024,720,1440) 100x100 dim=(lat,lon)", M * N, M * N * 8 + M * 100 * 100 * 8, best, med, "1/8 of the 8-GPU case")
+    x.free(); y.free()
+
+    # cfg5: 3 x fp64, non-uniform (50,60,70) bins, fp64 weights; whole 4e8 and the 1/8 shard
+    r = np.random.default_rng(12)
+    edges = []
+    for m in (51, 61, 71):
+        ee = np.sort(r.uniform(-4, 4, m)); ee[0], ee[-1] = -4.0, 4.0
+        edges.append(ee)
+    for frac, label in ((1.0, "whole"), (0.125, "1/8 shard")):
+        n = int(4e8 * sc * frac)
+        xs = [DeviceArray.normal((n,), np.float64, seed=8 + i) for i in range(3)]
+        w = DeviceArray.uniform((n,), np.float64, seed=11)
+        _, best, med = timed(xs, w, edges, None, a.reps)
+        report(f"cfg5 {label} 3xfp64 ({n:.3g},) fp64 w non-uniform (50,60,70)", n, n * 32 + 50 * 60 * 70 * 8, best, med)
+        for q in xs + [w]:
+            q.free()
+
+    with open(os.path.join(ROOT, "gpurun_out", "bench_configs.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -339,7 +339,7 @@ int enqueue(Ctx* c, const Prep& pr, Plan& pl) {
   else if (pl.zero == Plan::ZERO_SHARED) CU(xhk_launch_zero_shared_rows(pl.p, pl.l));
   if (pl.need_window && !pr.window_done) {
     const long long total = pl.p.M * pl.p.N;
-    const int n_probe = static_cast<int>(std::min<long long>(total, 1 << 14));
+    const int n_probe = static_cast<int>(std::min<long long>(total, 1 << 13));
     CU(xhk_launch_window(pl.p, pl.l, c->window, pl.window_budget, n_probe));
     pr.window_done = true;
   }

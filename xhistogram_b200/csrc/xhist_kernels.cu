@@ -390,15 +390,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 // of at most `budget` bins (XHK_WINDOW); (2) the fixed-point scale of the weights.  One CTA, ~10-20 us;
 // run once per call when the bin space exceeds shared memory or weights are present.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int KT>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant__ XhkParams p, XhkWindow* wout, int budget,
                                                            int n_probe) {
+  constexpr int KMAX = KT ? KT : XHK_MAX_VARS;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_moff[XHK_MAX_VARS + 1];
   __shared__ unsigned long long s_wmax;
   __shared__ int s_fail, s_seen;
   __shared__ double s_mul, s_limit;
-  const int K = p.n_vars, tid = threadIdx.x, nthr = blockDim.x;
+  const int K = KT ? KT : p.n_vars, tid = threadIdx.x, nthr = blockDim.x;
   T* sedges = reinterpret_cast<T*>(smem);
   unsigned int* marg = reinterpret_cast<unsigned int*>(smem + ((static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15)));
   for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
@@ -408,7 +409,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant
   for (int i = tid; i < mtot; i += nthr) marg[i] = 0u;
   __syncthreads();
   const long long total = p.M * p.N;
-  const long long step = total / n_probe > 0 ? total / n_probe : 1;
+  // probe positions: 256-sample contiguous runs spread evenly over the block (few pages touched: far-apart
+  // single-element probes cost ~100 us of TLB misses on multi-GB inputs)
+  const long long n_runs = (n_probe + 255) / 256;
+  const long long run_stride = total / n_runs;
+  auto probe_pos = [&](long long i) -> long long { return (i >> 8) * run_stride + (i & 255); };
   const bool flat = p.M == 1;
   auto locate = [&](long long pos, long long& r, long long& c) {
     if (flat) { r = 0; c = pos; } else { r = pos / p.N; c = pos - r * p.N; }
@@ -419,31 +424,36 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant
   };
   constexpr int PB = 8;  // probe positions in flight per thread
   unsigned long long wmx = 0ull;
-  double wkeep[2 * PB]; int nkeep = 0;   // this thread's probe weights (n_probe <= 2*PB*blockDim)
+  double wkeep[PB]; int nkeep = 0;        // this thread's probe weights (first batch; enough for the statistic)
   for (long long i0 = tid; i0 < n_probe; i0 += static_cast<long long>(PB) * nthr) {
-    T xs[PB][XHK_MAX_VARS]; double ws[PB]; bool have[PB];
+    T xs[PB][KMAX]; double ws[PB]; bool have[PB];
 #pragma unroll
     for (int b = 0; b < PB; ++b) {
       const long long i = i0 + static_cast<long long>(b) * nthr;
-      const long long pos = i * step;
+      const long long pos = probe_pos(i);
       have[b] = i < n_probe && pos < total;
       ws[b] = 0.0;
       if (have[b]) {
         long long r, c; locate(pos, r, c);
-        for (int k = 0; k < K; ++k) xs[b][k] = (static_cast<const T*>(p.data[k]) + r * p.stride[k])[c];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) if (k < K) xs[b][k] = (static_cast<const T*>(p.data[k]) + r * p.stride[k])[c];
         if (p.w_dtype != 0) ws[b] = wload(r, c);
       }
     }
 #pragma unroll
     for (int b = 0; b < PB; ++b) {
       if (have[b]) {
-        int j[XHK_MAX_VARS]; bool ok = true;
-        for (int k = 0; k < K; ++k) { j[k] = exact_bin_inline<T>(p, k, sedges, xs[b][k]); ok = ok && j[k] >= 0; }
-        if (ok) for (int k = 0; k < K; ++k) atomicAdd(&marg[s_moff[k] + j[k]], 1u);
+        int j[KMAX]; bool ok = true;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) if (k < K) { j[k] = exact_bin_inline<T>(p, k, sedges, xs[b][k]); ok = ok && j[k] >= 0; }
+        if (ok) {
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) if (k < K) atomicAdd(&marg[s_moff[k] + j[k]], 1u);
+        }
         if (p.w_dtype != 0) {
           const double a = fabs(ws[b]);
           if (a < INFINITY) { const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(a)); if (bits > wmx) wmx = bits; }
-          if (nkeep < 2 * PB) wkeep[nkeep++] = ws[b];
+          if (i0 == tid) { wkeep[b] = ws[b]; nkeep = b + 1; }
         }
       }
     }
@@ -465,9 +475,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant
     }
     __syncthreads();
     int fails = 0;
-    for (int i = 0; i < nkeep; ++i) {
-      const double vs = wkeep[i] * s_mul;
-      if (!((static_cast<double>(__double2ll_rn(vs)) == vs) & (fabs(vs) < s_limit))) ++fails;
+#pragma unroll
+    for (int i = 0; i < PB; ++i) {
+      if (i < nkeep) {
+        const double vs = wkeep[i] * s_mul;
+        if (!((static_cast<double>(__double2ll_rn(vs)) == vs) & (fabs(vs) < s_limit))) ++fails;
+      }
     }
     int seen = nkeep;
     for (int o = 16; o > 0; o >>= 1) { fails += __shfl_xor_sync(0xffffffffu, fails, o); seen += __shfl_xor_sync(0xffffffffu, seen, o); }
@@ -641,6 +654,19 @@ HistKernel pick(int dtype, int w_dtype, int K, bool fast) {
   return pick_k<double, 2>(K, fast);
 }
 
+typedef void (*WindowKernel)(const XhkParams, XhkWindow*, int, int);
+template <typename T>
+WindowKernel pick_window_t(int K) {
+  switch (K) {
+    case 1: return k_window<T, 1>;
+    case 2: return k_window<T, 2>;
+    case 3: return k_window<T, 3>;
+    case 4: return k_window<T, 4>;
+    default: return k_window<T, 0>;
+  }
+}
+WindowKernel pick_window(int dtype, int K) { return dtype == 1 ? pick_window_t<float>(K) : pick_window_t<double>(K); }
+
 }  // namespace
 
 cudaError_t xhk_set_smem_limits(int max_optin) {
@@ -652,9 +678,12 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
           if (e != cudaSuccess) return e;
         }
   // k_window has a little more static shared memory than k_hist
-  cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k_window<float>), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 192);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(reinterpret_cast<const void*>(k_window<double>), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 192);
+  for (int dt = 1; dt <= 2; ++dt)
+    for (int k = 0; k <= 4; ++k) {
+      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_window(dt, k)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 192);
+      if (e != cudaSuccess) return e;
+    }
+  return cudaSuccess;
 }
 
 cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l) {
@@ -672,8 +701,7 @@ size_t xhk_window_kernel_smem(const XhkParams& p) {
 
 cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow* window_dev, int budget_bins, int n_probe) {
   const size_t smem = xhk_window_kernel_smem(p);
-  if (l.dtype == 1) k_window<float><<<1, kMaxThreads, smem, l.stream>>>(p, window_dev, budget_bins, n_probe);
-  else k_window<double><<<1, kMaxThreads, smem, l.stream>>>(p, window_dev, budget_bins, n_probe);
+  pick_window(l.dtype, p.n_vars)<<<1, kMaxThreads, smem, l.stream>>>(p, window_dev, budget_bins, n_probe);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Turn one GPU round's ncu outputs (gpurun_out/<tag>_launches.csv, <tag>_prof_hist.ncu-rep) into the
+tracked summaries under profiles/ (launch-list shares, kernel metrics, DRAM traffic for bench.py).
+
+    python tools/make_profile_summary.py <tag> <round-label>
+"""
+import collections
+import csv
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag, rnd = sys.argv[1], sys.argv[2]
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+rep = os.path.join(G, f"{tag}_prof_hist.ncu-rep")
+for page in ("raw", "source"):
+    with open(os.path.join(G, f"{tag}_{page}.csv"), "w") as f:
+        subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], stdout=f, stderr=subprocess.DEVNULL, check=False)
+
+# ---- launch list shares
+rows = [r for r in csv.reader(open(os.path.join(G, f"{tag}_launches.csv"))) if len(r) > 10]
+hdr = rows[0]; ki = hdr.index("Kernel Name"); vi = hdr.index("Metric Value")
+launches = [(r[ki], float(r[vi].replace(",", ""))) for r in rows[1:]]
+out = [f"# {rnd} — ncu launch list of `python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 1 --samples 2.5e8`", "",
+       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv` (cold-cache, serialised: compare SHARES, not absolutes).",
+       f"Raw CSV: `profiles/{rnd}_launches.csv`.", ""]
+agg = collections.OrderedDict()
+for n, v in launches:
+    a = agg.setdefault(n.split("(")[0].replace("void <unnamed>::", ""), [0, 0.0, 0.0]); a[0] += 1; a[1] += v; a[2] = max(a[2], v)
+tot = sum(a[1] for a in agg.values())
+out += ["| kernel | launches | total ms | share | longest launch ms |", "|---|---|---|---|---|"]
+for n, (c, t, m) in agg.items():
+    out.append(f"| `{n}` | {c} | {t/1e6:.3f} | {100*t/tot:.1f}% | {m/1e6:.3f} |")
+big = [v for n, v in launches if "k_hist<float, 1" in n and v > 5e5]
+win = sorted(v for n, v in launches if "k_window" in n)
+if big and win:
+    kb, kw = sum(big) / len(big), win[len(win) // 2]
+    out += ["", f"Device-resident step (2.5e8 samples): `k_hist` {kb/1e6:.3f} ms per launch ({len(big)} launches), `k_window` median "
+            f"{kw/1e3:.1f} us -> `k_hist` is {100*kb/(kb+kw):.1f}% of the step's kernel time (bench.py's roofline uses the CUDA-event "
+            "time of both together).",
+            "The many short `k_hist` launches are the 8M-sample chunks of the end-to-end (host input) step; `k_fill` generates the synthetic inputs (untimed)."]
+open(os.path.join(P, f"{rnd}_launch_list.md"), "w").write("\n".join(out) + "\n")
+shutil.copy(os.path.join(G, f"{tag}_launches.csv"), os.path.join(P, f"{rnd}_launches.csv"))
+
+# ---- full capture summary
+rows = list(csv.reader(open(os.path.join(G, f"{tag}_raw.csv"))))
+hdr, units, vals = rows[0], rows[1], rows[2]
+g = lambda k: vals[hdr.index(k)]
+keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_shared_atom.sum", "smsp__inst_executed_op_global_red.sum",
+        "lts__t_sectors_srcunit_tex_op_red.sum", "lts__t_sectors_srcunit_tex_op_red_lookup_miss.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+kname = g("Kernel Name") if "Kernel Name" in hdr else "k_hist"
+md = [f"# {rnd} — `ncu --set full` capture of the dominant kernel", "", f"Kernel: `{kname}`", "",
+      "Command: `ncu --set full --clock-control none --import-source on -k regex:k_hist -s 5 -c 1 python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1`",
+      "(config 3: 1e9 samples, 2 x fp32 + fp32 weights, 256x256 bins; one launch). The .ncu-rep is kept out of git (17 MB); the numbers below were",
+      "read from it with `ncu -i ... --page raw --csv` / `--page source --csv` by `tools/make_profile_summary.py`.", "",
+      "| metric | value | unit |", "|---|---|---|"]
+for k in keys:
+    if k in hdr:
+        md.append(f"| `{k}` | {g(k)} | {units[hdr.index(k)]} |")
+md += ["", "Warp stall reasons (warps per issue-active cycle):", ""]
+for i, h in enumerate(hdr):
+    if "smsp__average_warps_issue_stalled" in h and "per_issue_active" in h and float(vals[i]) > 0.1:
+        md.append(f"* {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')}: {float(vals[i]):.2f}")
+mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
+traffic = float(g("dram__bytes_read.sum")) * mult[units[hdr.index("dram__bytes_read.sum")]] + \
+    float(g("dram__bytes_write.sum")) * mult[units[hdr.index("dram__bytes_write.sum")]]
+inst = float(g("smsp__inst_executed.sum"))
+md += ["", f"DRAM traffic per launch: {traffic/1e9:.4f} GB read+write vs 12.0005 GB algorithmic -> no re-reads (ratio {traffic/12000524288:.4f}).",
+       f"Instructions: {inst:.3e} warp instructions = {inst*32/1e9:.1f} SASS instructions per sample; issue-active "
+       f"{g('smsp__issue_active.avg.pct_of_peak_sustained_active')} % -> the kernel is bound by instruction issue, not by DRAM "
+       f"({g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')} % of DRAM peak).", "Tensor pipe: 0 % (by design: scatter/reduce)."]
+rows = list(csv.reader(open(os.path.join(G, f"{tag}_source.csv")))); h2 = rows[1]
+ia = h2.index("Source"); ie = h2.index("Instructions Executed"); iss = h2.index("Warp Stall Sampling (All Samples)")
+ops = collections.Counter(); tot = 0; body = []
+for r in rows[2:]:
+    if len(r) <= iss:
+        continue
+    m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[ia].strip()); op = m.group(2) if m else "?"
+    op = op if op.startswith("ATOMS") or op.startswith("REDG") else op.split(".")[0]
+    n = int(r[ie] or 0); ops[op] += n; tot += n; body.append((int(r[iss] or 0), n, r[ia].strip()))
+md += ["", "SASS opcode mix (executed warp instructions, top 16):", "", "| opcode | share |", "|---|---|"]
+for op, n in ops.most_common(16):
+    md.append(f"| `{op}` | {100*n/tot:.1f}% |")
+md += ["", "Instructions with the most stall samples:", "", "| stall samples | executed | SASS |", "|---|---|---|"]
+for s_, n, src in sorted(body, reverse=True)[:10]:
+    md.append(f"| {s_} | {n} | `{src[:90]}` |")
+open(os.path.join(P, f"{rnd}_ncu_k_hist_summary.md"), "w").write("\n".join(md) + "\n")
+json.dump({"kernel": kname, "samples": 1000000000, "dram_bytes_per_launch": traffic,
+           "source": f"profiles/{rnd}_ncu_k_hist_summary.md (ncu --set full)"}, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
+print("\n".join(md[:60]))
+print("\n".join(out))

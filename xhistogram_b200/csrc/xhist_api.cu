@@ -150,6 +150,37 @@ template <> struct CSel<float> { static float* row(XhkParams& p, int k) { return
 template <> struct CSel<double> { static double* row(XhkParams& p, int k) { return p.cd[k]; } };
 
 // Fill the classification constants of variable k; append its effective edges to `table`.
+template <typename T> void set_lut_inv(XhkParams& p, int k, long double v);
+template <> void set_lut_inv<float>(XhkParams& p, int k, long double v) { p.lut_invf[k] = static_cast<float>(v); }
+template <> void set_lut_inv<double>(XhkParams& p, int k, long double v) { p.lut_invd[k] = static_cast<double>(v); }
+
+// Lookup table of a non-uniform variable: G equal cells over [lo, hi]; entry c = (#effective edges <= left
+// boundary of cell c) - 1.  The device brackets its search with the entries of cells c-1 and c+2, so a
+// rounding error of up to one cell in the device's cell index cannot exclude the true bin.
+template <typename T>
+void build_lut(int k, XhkParams& p, const std::vector<T>& table, std::vector<unsigned short>& lut) {
+  const int nb = p.nb[k];
+  p.lut_n[k] = 0; p.lut_off[k] = static_cast<int>(lut.size());
+  if (p.uniform[k] || nb < 8 || nb > 60000) return;
+  const T* e = table.data() + p.eoff[k];
+  const long double lo = e[0], hi = e[nb];
+  if (!std::isfinite(static_cast<double>(lo)) || !std::isfinite(static_cast<double>(hi)) || !(hi > lo)) return;
+  int G = 64; while (G < 8 * nb && G < 4096) G <<= 1;
+  const long double inv = G / (hi - lo);
+  if (!std::isfinite(static_cast<double>(inv)) || !(inv > 0)) return;
+  // keep the device's cell index within one cell of the exact one: G * (few ulp) must stay far below 1
+  if (static_cast<long double>(G) * (sizeof(T) == 4 ? 6e-7L : 1e-15L) > 0.05L) return;
+  set_lut_inv<T>(p, k, inv);
+  for (int c = 0; c < G; ++c) {
+    const long double b = lo + c * (hi - lo) / G;
+    const T* it = std::upper_bound(e, e + nb + 1, b, [](long double v, T edge) { return v < static_cast<long double>(edge); });
+    int cnt = static_cast<int>(it - e);
+    if (cnt < 1) cnt = 1;
+    lut.push_back(static_cast<unsigned short>(std::min(cnt - 1, nb)));
+  }
+  p.lut_n[k] = G;
+}
+
 template <typename T>
 int prep_var(const double* e, int E, int k, bool force_search, XhkParams& p, std::vector<T>& table) {
   for (int j = 0; j < E; ++j) if (std::isnan(e[j])) return fail(XH_ERR_INVALID, "edges of variable %d contain NaN", k);
@@ -206,8 +237,9 @@ struct Plan {
 // effective-edge table (uploaded once), bin-space geometry.
 struct Prep {
   XhkParams base;
-  std::vector<unsigned char> edge_host;
-  size_t edges_al = 0;
+  std::vector<unsigned char> edge_host;   // effective edges followed (16-byte aligned) by the lookup tables
+  size_t edges_al = 0;                     // shared-memory bytes of edges + tables
+  size_t lut_dev_off = 0;                  // byte offset of the tables inside edge_host / the device buffer
   mutable bool window_done = false;   // the shared-memory window is chosen on the first block of a call and reused
 };
 
@@ -236,9 +268,17 @@ int prep_call(const xh_desc* d, Prep& pr) {
   for (int k = K - 1; k >= 0; --k) { p.gmul[k] = mul; mul *= p.nb[k]; }
   p.n_edges_total = static_cast<int>(d->dtype == XH_F32 ? tf.size() : td.size());
   const size_t edge_bytes = p.n_edges_total * tsz;
-  pr.edge_host.resize(edge_bytes);
+  std::vector<unsigned short> lut;
+  for (int k = 0; k < K; ++k) {
+    if (d->flags & XH_FLAG_FORCE_SEARCH) { p.lut_n[k] = 0; p.lut_off[k] = 0; continue; }
+    if (d->dtype == XH_F32) build_lut<float>(k, p, tf, lut); else build_lut<double>(k, p, td, lut);
+  }
+  p.n_lut_total = static_cast<int>(lut.size());
+  pr.lut_dev_off = (edge_bytes + 15) & ~static_cast<size_t>(15);
+  pr.edge_host.assign(pr.lut_dev_off + lut.size() * 2, 0);
   std::memcpy(pr.edge_host.data(), d->dtype == XH_F32 ? static_cast<const void*>(tf.data()) : static_cast<const void*>(td.data()), edge_bytes);
-  pr.edges_al = (edge_bytes + 15) & ~static_cast<size_t>(15);
+  if (!lut.empty()) std::memcpy(pr.edge_host.data() + pr.lut_dev_off, lut.data(), lut.size() * 2);
+  pr.edges_al = pr.lut_dev_off + ((lut.size() * 2 + 15) & ~static_cast<size_t>(15));
   return XH_OK;
 }
 
@@ -266,6 +306,7 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
   p.out = d->out;
   p.window = c->window;
   p.edges = c->edges;
+  p.lut = reinterpret_cast<const unsigned short*>(static_cast<const unsigned char*>(c->edges) + pr.lut_dev_off);
   const long long B = p.B;
 
   // shared-memory budget
@@ -273,7 +314,7 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
   const size_t item = d->w_dtype == XH_NONE ? 4 : 8;
   const long long budget1 = static_cast<long long>(c->smem_optin) - 64 - static_cast<long long>(edges_al);  // 1 CTA / SM
   if (budget1 < 0) return fail(XH_ERR_UNSUPPORTED, "bin edges (%zu bytes) do not fit in shared memory", pr.edge_host.size());
-  const long long cap1 = budget1 / static_cast<long long>(item);
+  const long long cap1 = budget1 / static_cast<long long>(item) - 32;   // 32 trash slots (see k_hist)
   int mode;
   if (d->flags & XH_FLAG_FORCE_GLOBAL) mode = XHK_GLOBAL;
   else if (B <= cap1 && !(d->flags & XH_FLAG_FORCE_WINDOW)) mode = XHK_FULL;
@@ -283,9 +324,9 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
   p.hist_mode = mode;
 
   int ctas_per_sm = 1, threads = XHK_THREADS;   // k_hist is compiled for <= XHK_THREADS threads per CTA
-  size_t smem = edges_al;
+  size_t smem = edges_al + 32 * item;           // XHK_GLOBAL: only the trash slots
   if (mode == XHK_FULL) {
-    smem = edges_al + static_cast<size_t>(B) * item;
+    smem = edges_al + static_cast<size_t>(B + 32) * item;
     // two 512-thread CTAs per SM when both histograms fit (a flush of one overlaps the stream of the other)
     if (2 * (smem + 1024 + 64) <= static_cast<size_t>(c->smem_per_sm)) { ctas_per_sm = 2; threads = XHK_THREADS / 2; }
     p.hist_capacity = static_cast<int>(B);
@@ -293,7 +334,7 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
     long long cap = cap1;
     if (d->flags & XH_FLAG_FORCE_WINDOW) cap = std::max<long long>(1, std::min<long long>(cap1, B / 3));
     pl.need_window = true; pl.window_budget = static_cast<int>(std::min<long long>(cap, 1ll << 30));
-    smem = edges_al + static_cast<size_t>(pl.window_budget) * item;
+    smem = edges_al + static_cast<size_t>(pl.window_budget + 32) * item;
     p.hist_capacity = pl.window_budget;
   } else {
     ctas_per_sm = 2; threads = XHK_THREADS / 2;

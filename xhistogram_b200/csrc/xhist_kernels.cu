@@ -77,20 +77,45 @@ __device__ __forceinline__ bool uniform_guess(const XhkParams& p, int k, T x, in
 }
 
 // exact bin of any sample (slow but general): range test, uniform guess when usable, else search
+template <typename T> __device__ __forceinline__ T lut_inv(const XhkParams& p, int k);
+template <> __device__ __forceinline__ float lut_inv<float>(const XhkParams& p, int k) { return p.lut_invf[k]; }
+template <> __device__ __forceinline__ double lut_inv<double>(const XhkParams& p, int k) { return p.lut_invd[k]; }
+
+// Non-uniform edges: the cell of x in a uniform partition of [lo, hi] brackets #{e_j <= x} between the table
+// entries of cell c-1 and cell c+2 (one cell of slack on either side absorbs the rounding of the cell index),
+// so the binary search runs over a handful of edges instead of all of them.
 template <typename T>
-__device__ __forceinline__ int exact_bin_inline(const XhkParams& p, int k, const T* __restrict__ sedges, T x) {
+__device__ __forceinline__ int lut_bin(const XhkParams& p, int k, const T* __restrict__ e, const unsigned short* __restrict__ lut, T x) {
+  const int nb = p.nb[k], G = p.lut_n[k];
+  int c = floor_to_int((x - Consts<T>::get(p, k, XHK_C_LO)) * lut_inv<T>(p, k));
+  c = max(0, min(c, G - 1));
+  int lo = static_cast<int>(lut[max(c - 1, 0)]) + 1;                       // e[lo-1] <= x is known
+  int hi = (c + 2 < G) ? static_cast<int>(lut[c + 2]) + 1 : nb + 1;         // #{e_j <= x} <= hi
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (e[mid - 1] <= x) lo = mid; else hi = mid - 1;
+  }
+  const int b = lo - 1;
+  return b > nb - 1 ? nb - 1 : b;
+}
+
+template <typename T>
+__device__ __forceinline__ int exact_bin_inline(const XhkParams& p, int k, const T* __restrict__ sedges,
+                                                const unsigned short* __restrict__ slut, T x) {
   if (!(x >= Consts<T>::get(p, k, XHK_C_LO) && x <= Consts<T>::get(p, k, XHK_C_HI))) return -1;  // NaN: dropped (rule R3)
   const int nb = p.nb[k];
   if (p.uniform[k]) {
     int j;
     if (uniform_guess<T>(p, k, x, j) && static_cast<unsigned>(j) < static_cast<unsigned>(nb)) return j;
   }
+  if (p.lut_n[k]) return lut_bin<T>(p, k, sedges + p.eoff[k], slut + p.lut_off[k], x);
   return search_bin<T>(sedges + p.eoff[k], nb, x);
 }
 // out-of-line copy for the rare exact path of the fast kernel (keeps its hot loop small)
 template <typename T>
-__device__ __noinline__ int exact_bin(const XhkParams& p, int k, const T* __restrict__ sedges, T x) {
-  return exact_bin_inline<T>(p, k, sedges, x);
+__device__ __noinline__ int exact_bin(const XhkParams& p, int k, const T* __restrict__ sedges,
+                                      const unsigned short* __restrict__ slut, T x) {
+  return exact_bin_inline<T>(p, k, sedges, slut, x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -128,9 +153,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   const int K = KT ? KT : p.n_vars;
   const int tid = threadIdx.x, nthr = blockDim.x;
   T* sedges = reinterpret_cast<T*>(smem);
-  HT* shist = reinterpret_cast<HT*>(smem + ((static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15)));
+  const size_t edges_al = (static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15);
+  unsigned short* slut = reinterpret_cast<unsigned short*>(smem + edges_al);
+  HT* shist = reinterpret_cast<HT*>(smem + edges_al + ((static_cast<size_t>(p.n_lut_total) * 2 + 15) & ~static_cast<size_t>(15)));
 
   for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
+  for (int i = tid; i < p.n_lut_total; i += nthr) slut[i] = p.lut[i];
   if (tid < XHK_MAX_VARS) {
     int lo = 0, len = 0;
     if (tid < K) {
@@ -146,7 +174,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   for (int k = 0; k < KMAX; ++k) {
     if (k < K) { wlo[k] = s_wlo[k]; wlen[k] = s_wlen[k]; wtot *= wlen[k]; } else { wlo[k] = 0; wlen[k] = 0; }
   }
-  for (int i = tid; i < wtot; i += nthr) shist[i] = HT(0);
+  for (int i = tid; i < (W == 0 ? wtot : wtot + 32); i += nthr) shist[i] = HT(0);
   // weighted accumulation mode (uniform for the launch): exact fixed point in two u32 limbs, or float64 adds
   bool fx = false; WT fx_mul = WT(0), fx_limit = WT(0); double fx_unmul = 0.0;
   if constexpr (W != 0) {
@@ -154,8 +182,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       fx = true; fx_mul = static_cast<WT>(p.window->fx_mul); fx_limit = static_cast<WT>(p.window->fx_limit); fx_unmul = p.window->fx_unmul;
     }
   }
+  // fixed-point layout: [wtot low limbs][32 trash slots][wtot high limbs][32 trash slots]; a lane with nothing
+  // to add puts a zero into its own trash slot, which keeps the weighted shared adds free of branches
+  const int wcap = wtot + 32;
   const unsigned sh_lo = static_cast<unsigned>(__cvta_generic_to_shared(shist));   // counts / lo limbs / doubles
-  const unsigned sh_hi = sh_lo + 4u * static_cast<unsigned>(wtot);                  // hi limbs (fixed point)
+  const unsigned sh_hi = sh_lo + 4u * static_cast<unsigned>(wcap);                  // hi limbs (fixed point)
+  const unsigned trash = static_cast<unsigned>(wtot + (tid & 31));
   __syncthreads();
 
   OT* const out = static_cast<OT*>(p.out);
@@ -180,7 +212,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k < K) {
-        j[k] = FAST ? exact_bin<T>(p, k, sedges, x[k]) : exact_bin_inline<T>(p, k, sedges, x[k]);
+        j[k] = FAST ? exact_bin<T>(p, k, sedges, slut, x[k]) : exact_bin_inline<T>(p, k, sedges, slut, x[k]);
         ok = ok && (j[k] >= 0);
         const unsigned jw = static_cast<unsigned>(j[k] - wlo[k]);
         inwin = inwin && (jw < static_cast<unsigned>(wlen[k]));   // also false for j == -1
@@ -356,8 +388,41 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             }
           }
         }
+        if (W != 0 && fx) {
+          // fixed-point shared adds, straight-line: 4 low-limb ATOMS back to back, then the 4 high-limb REDs
+          // (each takes the carry from the value its ATOMS returned)
+          unsigned inexact = 0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) shared_add4(wb[u], wv[u], out_row);
+          for (int u = 0; u < U; ++u) {
+            unsigned idx[4], lo[4], hi[4], old[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const WT vs = wv[u][e] * fx_mul;
+              const long long v = to_ll_rn(vs);
+              const bool exact = (static_cast<WT>(v) == vs) & (fabs(vs) < fx_limit);
+              const bool valid = wb[u][e] >= 0;
+              const bool ok = valid & exact;
+              inexact |= (valid & !exact) ? (1u << (4 * u + e)) : 0u;
+              idx[e] = ok ? static_cast<unsigned>(wb[u][e]) : trash;
+              lo[e] = ok ? static_cast<unsigned>(v) : 0u;
+              hi[e] = ok ? static_cast<unsigned>(static_cast<unsigned long long>(v) >> 32) : 0u;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) old[e] = atoms_add_u32(sh_lo + 4u * idx[e], lo[e]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) reds_add_u32(sh_hi + 4u * idx[e], hi[e] + ((old[e] + lo[e] < old[e]) ? 1u : 0u));
+          }
+          if (inexact) {   // rare: weights that are not exact multiples of the scale -> float64 global RED
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (inexact & (1u << (4 * u + e))) global_add(out_row, window_to_global(wb[u][e]), static_cast<double>(wv[u][e]));
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) shared_add4(wb[u], wv[u], out_row);
+        }
       }
     }
     s += len;
@@ -368,7 +433,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       const bool full = p.hist_mode == XHK_FULL;
       const bool owned = full && p.store_owned_rows && c0 == 0 && len == p.N;
       unsigned int* lo32 = reinterpret_cast<unsigned int*>(shist);
-      unsigned int* hi32 = lo32 + wtot;
+      unsigned int* hi32 = lo32 + wcap;
       for (int b = tid; b < wtot; b += nthr) {
         OT v; bool nz;
         if constexpr (W == 0) { v = static_cast<OT>(shist[b]); nz = v != 0; shist[b] = 0u; }
@@ -401,8 +466,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant
   __shared__ double s_mul, s_limit;
   const int K = KT ? KT : p.n_vars, tid = threadIdx.x, nthr = blockDim.x;
   T* sedges = reinterpret_cast<T*>(smem);
-  unsigned int* marg = reinterpret_cast<unsigned int*>(smem + ((static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15)));
+  const size_t edges_al = (static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15);
+  unsigned short* slut = reinterpret_cast<unsigned short*>(smem + edges_al);
+  unsigned int* marg = reinterpret_cast<unsigned int*>(smem + edges_al + ((static_cast<size_t>(p.n_lut_total) * 2 + 15) & ~static_cast<size_t>(15)));
   for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
+  for (int i = tid; i < p.n_lut_total; i += nthr) slut[i] = p.lut[i];
   if (tid == 0) { int o = 0; for (int k = 0; k < K; ++k) { s_moff[k] = o; o += p.nb[k]; } s_moff[K] = o; s_wmax = 0ull; s_fail = 0; s_seen = 0; }
   __syncthreads();
   const int mtot = s_moff[K];
@@ -445,7 +513,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant
       if (have[b]) {
         int j[KMAX]; bool ok = true;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) if (k < K) { j[k] = exact_bin_inline<T>(p, k, sedges, xs[b][k]); ok = ok && j[k] >= 0; }
+        for (int k = 0; k < KMAX; ++k) if (k < K) { j[k] = exact_bin_inline<T>(p, k, sedges, slut, xs[b][k]); ok = ok && j[k] >= 0; }
         if (ok) {
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) if (k < K) atomicAdd(&marg[s_moff[k] + j[k]], 1u);
@@ -694,7 +762,7 @@ cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l) {
 
 size_t xhk_window_kernel_smem(const XhkParams& p) {
   size_t tsz = 8;  // upper bound on sizeof(T)
-  size_t e = (static_cast<size_t>(p.n_edges_total) * tsz + 15) & ~static_cast<size_t>(15);
+  size_t e = ((static_cast<size_t>(p.n_edges_total) * tsz + 15) & ~static_cast<size_t>(15)) + ((static_cast<size_t>(p.n_lut_total) * 2 + 15) & ~static_cast<size_t>(15));
   size_t m = 0; for (int k = 0; k < p.n_vars; ++k) m += static_cast<size_t>(p.nb[k]) * 4;
   return e + m;
 }

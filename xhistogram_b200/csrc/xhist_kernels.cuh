@@ -56,6 +56,14 @@ struct XhkParams {
   long long gmul[XHK_MAX_VARS];     // C-order multipliers of the global bin index
   const void* edges;                // device, typed T, all variables concatenated
   int n_edges_total;
+  // non-uniform variables: lookup table over lut_n[k] equal cells of [lo, hi]; entry c = bin at the left boundary
+  // of cell c.  It brackets the binary search to the edges between cells c-1 and c+2 (usually 1-2 steps).
+  const unsigned short* lut;        // device, all variables concatenated
+  int n_lut_total;
+  int lut_n[XHK_MAX_VARS];          // cells (0 = no table: plain binary search)
+  int lut_off[XHK_MAX_VARS];
+  float lut_invf[XHK_MAX_VARS];     // cells per unit of x, fp32 / fp64 kernels
+  double lut_invd[XHK_MAX_VARS];
   int n_vars;
   void* out;                        // int64 (no weights) or double (weights), [M][B]
   long long B;                      // bins per row

@@ -202,3 +202,70 @@ def test_multi_gpu_in_process(gpu_count):
     xr = x[:4_000_000].reshape(40, 100_000)
     h, _ = core.histogram(xr, bins=e, axis=1, devices=list(range(gpu_count)))
     assert np.array_equal(h, O.histogram(xr, bins=e, axis=1)[0])
+
+
+@pytest.mark.parametrize("kind", ["wide_dynamic_range", "full_mantissa_f64", "negative_mixed", "all_zero", "huge", "tiny", "inf_nan_inside"])
+def test_weight_accumulation_modes(kind):
+    """Weights that exercise the fixed-point scale selection, its float64 fallback and the inexact-weight spill."""
+    r = np.random.default_rng(31)
+    n = 400_000
+    x = r.standard_normal(n).astype(np.float32)
+    y = r.standard_normal(n).astype(np.float32)
+    if kind == "wide_dynamic_range":
+        w = np.exp(r.uniform(-40, 40, n)).astype(np.float32)          # 35 decades: most weights inexact at any one scale
+    elif kind == "full_mantissa_f64":
+        w = r.random(n)                                                # 53-bit mantissas: probe must choose float64 adds
+    elif kind == "negative_mixed":
+        w = r.standard_normal(n).astype(np.float32)
+    elif kind == "all_zero":
+        w = np.zeros(n, np.float32)
+    elif kind == "huge":
+        w = (r.random(n) * 1e30).astype(np.float32)
+    elif kind == "tiny":
+        w = (r.random(n) * 1e-30).astype(np.float32)
+    else:
+        w = r.random(n).astype(np.float32)
+        w[:50] = np.inf; w[50:100] = -np.inf; w[100:150] = np.nan
+    for bins in ([np.linspace(-4, 4, 33)] * 2, [np.linspace(-4, 4, 257)] * 2):     # full and windowed shared histograms
+        want = O.block_bincount([x[None], y[None]], bins, w[None])[0]
+        with np.errstate(invalid="ignore"):
+            h, _ = core.histogram(x, y, bins=bins, weights=w)
+        assert h.shape == want.shape
+        if kind == "inf_nan_inside":
+            # +inf and -inf in one bin give NaN in any order; elsewhere the usual bar
+            assert np.array_equal(np.isnan(h), np.isnan(want))
+            m = np.isfinite(want)
+            assert np.array_equal(np.isinf(h), np.isinf(want))
+            np.testing.assert_allclose(h[m], want[m], rtol=1e-6, atol=0)
+        elif kind == "negative_mixed":
+            # cancellation: compare against the scale of the terms (the float64 sum order differs from numpy's)
+            scale = O.block_bincount([x[None], y[None]], bins, np.abs(w)[None])[0]
+            assert np.all(np.abs(h - want) <= 1e-9 * np.maximum(scale, 1e-300))
+        else:
+            assert_hist_equal(h, want, rtol=1e-6)
+
+
+def test_row_regimes_device_resident():
+    """Rows on the device in three regimes: many short rows, few long rows, odd (unaligned) row lengths."""
+    for M, N, nb in ((5000, 64, 10), (3, 1_000_003, 200), (257, 4099, 64)):
+        x = DeviceArray.normal((M, N), np.float32, seed=41)
+        w = DeviceArray.uniform((M, N), np.float32, seed=42)
+        e = np.linspace(-3, 3, nb + 1)
+        xn, wn = x.to_numpy(), w.to_numpy()
+        h, _ = core.histogram(x, bins=e, axis=1)
+        assert np.array_equal(h, O.histogram(xn, bins=e, axis=1)[0])
+        hw, _ = core.histogram(x, bins=e, axis=1, weights=w)
+        assert_hist_equal(hw, O.histogram(xn, bins=e, axis=1, weights=wn)[0])
+        x.free(); w.free()
+
+
+def test_cabi_rejects_bad_requests():
+    x = np.zeros(10, np.float32)
+    with pytest.raises(ValueError, match="monotonically"):
+        core._desc_call([x.reshape(1, -1)], [10], None, 0, [np.array([0.0, 2.0, 1.0])], 1, 10, _cabi.XH_F32, _cabi.XH_NONE,
+                        _cabi.XH_HOST, 0, None, 0, None)
+    with pytest.raises(ValueError):
+        core._desc_call([x.reshape(1, -1)], [10], None, 0, [np.array([0.0, np.nan])], 1, 10, _cabi.XH_F32, _cabi.XH_NONE,
+                        _cabi.XH_HOST, 0, None, 0, None)
+    h, _ = core.histogram(x, bins=np.array([1.0]))       # a single edge means zero bins, as in numpy
+    assert h.shape == (0,)

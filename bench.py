@@ -151,14 +151,33 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route everything written to fd 1 (NCCL banners, library chatter) to stderr; the JSON line goes to the saved fd."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -243,7 +262,23 @@ def main():
         rel = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
         parity = {"slab_samples": m, "counts_bit_exact": bool(np.array_equal(gc, wc)), "weighted_density_max_rel_err": rel}
         if not parity["counts_bit_exact"] or rel > 1e-6:
-            print(json.dumps({"error": "parity check failed", "parity": parity}), flush=True)
+            emit({"error": "parity check failed", "parity": parity})
+            return 1
+
+    # ---- multi-GPU invariant (outside the timed region): the all-reduced COUNT histogram must hold exactly the
+    #      sum over ranks of the local in-range counts (int64, bit-exact through ncclAllReduce)
+    if comm is not None:
+        import torch
+        hg, _ = D.histogram(x, y, bins=bins, comm=comm, sharded_axis=0)
+        hl, _ = core.histogram(x, y, bins=bins)
+        t = torch.tensor([int(hl.sum())], dtype=torch.int64, device=f"cuda:{dev}")
+        dist.all_reduce(t)
+        ok = int(hg.sum()) == int(t.item()) and hg.dtype == np.int64 and bool((hg >= hl).all())
+        if rank == 0:
+            parity["allreduce_counts_exact"] = bool(ok)
+        if not ok:
+            if rank == 0:
+                emit({"error": "all-reduced histogram does not match the per-rank totals", "parity": parity})
             return 1
 
     sampler = ClockSampler(dev)
@@ -351,7 +386,7 @@ def main():
         "parity": parity,
         "hbm_gbs_whole_step": alg_bytes / (ms_per_step * 1e-3) / 1e9,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

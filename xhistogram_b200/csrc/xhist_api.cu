@@ -160,25 +160,40 @@ template <> void set_lut_inv<double>(XhkParams& p, int k, long double v) { p.lut
 template <typename T>
 void build_lut(int k, XhkParams& p, const std::vector<T>& table, std::vector<unsigned short>& lut) {
   const int nb = p.nb[k];
-  p.lut_n[k] = 0; p.lut_off[k] = static_cast<int>(lut.size());
-  if (p.uniform[k] || nb < 8 || nb > 60000) return;
+  p.lut_n[k] = 0; p.lut_steps[k] = 0; p.lut_off[k] = static_cast<int>(lut.size());
+  if (p.uniform[k] || nb < 4 || nb > 60000) return;
   const T* e = table.data() + p.eoff[k];
   const long double lo = e[0], hi = e[nb];
   if (!std::isfinite(static_cast<double>(lo)) || !std::isfinite(static_cast<double>(hi)) || !(hi > lo)) return;
-  int G = 64; while (G < 8 * nb && G < 4096) G <<= 1;
+  auto count_le = [&](long double b) {   // #{effective edges <= b}
+    const T* it = std::upper_bound(e, e + nb + 1, b, [](long double v, T edge) { return v < static_cast<long double>(edge); });
+    return static_cast<int>(it - e);
+  };
+  // grow the table until no 3 consecutive cells hold more than 4 edges (then the device needs no search loop)
+  int G = 64; while (G < 16 * nb && G < 8192) G <<= 1;
+  std::vector<int> cnt;
+  int steps = 0;
+  for (;; G <<= 1) {
+    // keep the device's cell index within one cell of the exact one: G * (few ulp) must stay far below 1
+    if (static_cast<long double>(G) * (sizeof(T) == 4 ? 6e-7L : 1e-15L) > 0.05L) { if (G > 64) G >>= 1; break; }
+    cnt.assign(G + 1, 0);
+    for (int c = 0; c <= G; ++c) cnt[c] = std::max(1, count_le(c == G ? hi : lo + c * (hi - lo) / G));
+    steps = 0;
+    for (int c = 0; c < G; ++c) steps = std::max(steps, cnt[std::min(c + 2, G)] - cnt[std::max(c - 1, 0)]);
+    if (steps <= 4 || G >= 8192) break;
+  }
+  if (cnt.size() != static_cast<size_t>(G) + 1) {
+    cnt.assign(G + 1, 0);
+    for (int c = 0; c <= G; ++c) cnt[c] = std::max(1, count_le(c == G ? hi : lo + c * (hi - lo) / G));
+    steps = 0;
+    for (int c = 0; c < G; ++c) steps = std::max(steps, cnt[std::min(c + 2, G)] - cnt[std::max(c - 1, 0)]);
+  }
   const long double inv = G / (hi - lo);
   if (!std::isfinite(static_cast<double>(inv)) || !(inv > 0)) return;
-  // keep the device's cell index within one cell of the exact one: G * (few ulp) must stay far below 1
-  if (static_cast<long double>(G) * (sizeof(T) == 4 ? 6e-7L : 1e-15L) > 0.05L) return;
   set_lut_inv<T>(p, k, inv);
-  for (int c = 0; c < G; ++c) {
-    const long double b = lo + c * (hi - lo) / G;
-    const T* it = std::upper_bound(e, e + nb + 1, b, [](long double v, T edge) { return v < static_cast<long double>(edge); });
-    int cnt = static_cast<int>(it - e);
-    if (cnt < 1) cnt = 1;
-    lut.push_back(static_cast<unsigned short>(std::min(cnt - 1, nb)));
-  }
+  for (int c = 0; c < G; ++c) lut.push_back(static_cast<unsigned short>(std::min(cnt[c] - 1, nb)));
   p.lut_n[k] = G;
+  p.lut_steps[k] = (steps >= 1 && steps <= 4) ? steps : (steps == 0 ? 1 : 0);
 }
 
 template <typename T>
@@ -270,10 +285,12 @@ int prep_call(const xh_desc* d, Prep& pr) {
   const size_t edge_bytes = p.n_edges_total * tsz;
   std::vector<unsigned short> lut;
   for (int k = 0; k < K; ++k) {
-    if (d->flags & XH_FLAG_FORCE_SEARCH) { p.lut_n[k] = 0; p.lut_off[k] = 0; continue; }
+    if (d->flags & XH_FLAG_FORCE_SEARCH) { p.lut_n[k] = 0; p.lut_off[k] = 0; p.lut_steps[k] = 0; continue; }
     if (d->dtype == XH_F32) build_lut<float>(k, p, tf, lut); else build_lut<double>(k, p, td, lut);
   }
   p.n_lut_total = static_cast<int>(lut.size());
+  p.all_branch_free = (p.B < 2147483646ll) ? 1 : 0;
+  for (int k = 0; k < K; ++k) p.all_branch_free = p.all_branch_free && (p.uniform[k] || p.lut_steps[k] > 0);
   pr.lut_dev_off = (edge_bytes + 15) & ~static_cast<size_t>(15);
   pr.edge_host.assign(pr.lut_dev_off + lut.size() * 2, 0);
   std::memcpy(pr.edge_host.data(), d->dtype == XH_F32 ? static_cast<const void*>(tf.data()) : static_cast<const void*>(td.data()), edge_bytes);

@@ -138,11 +138,15 @@ template <> struct WType<2> { using type = double; };
 // the histogram kernel
 //   T    : data type (float / double)        W : 0 no weights, 1 fp32 weights, 2 fp64 weights
 //   KT   : number of variables at compile time (1..4), or 0 = runtime p.n_vars (scalar loads only)
-//   FAST : every variable has evenly spaced edges -> branch-free classification of 4 samples at a
-//          time; samples that are uncertain or fall outside the shared window take a side path
+//   MODE : 0 general (per-sample exact classification: range test, uniform guess / table-bracketed search)
+//          1 every variable has evenly spaced edges -> branch-free arithmetic classification of 8 samples at a
+//            time; samples that are uncertain or fall outside the shared window take a side path
+//          2 every variable is uniform or has a bounded-step lookup table -> branch-free classification of
+//            4 samples at a time, window spills as inline global REDs
 // ---------------------------------------------------------------------------------------------
-template <typename T, int W, int KT, bool FAST>
+template <typename T, int W, int KT, int MODE>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__ XhkParams p) {
+  constexpr bool FAST = (MODE == 1);
   using HT = typename std::conditional<W == 0, unsigned int, double>::type;          // shared accumulator
   using OT = typename std::conditional<W == 0, unsigned long long, double>::type;    // global accumulator
   using WT = typename WType<W>::type;
@@ -326,7 +330,86 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
           if constexpr (W == 0) { wv[u][0] = wv[u][1] = wv[u][2] = wv[u][3] = WT(1); }
         }
         int wb[U][4];
-        if constexpr (FAST) {
+        if constexpr (MODE == 2) {
+          // ---- branch-free classification for mixed uniform / non-uniform variables.
+          // Non-uniform: the table entry of cell c-1 is a bin at or below the sample's; at most lut_steps edges
+          // lie between that cell's left boundary and the sample, so that many compare-and-advance steps give
+          // the exact bin.  The steps run over the 4 samples of a group together (independent LDS chains).
+          unsigned unsure = 0;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool live = g + static_cast<long long>(u) * nthr < nvec;
+            int jb[KMAX][4]; bool okr[4], cert[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { okr[e] = live; cert[e] = live; }
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              if (p.uniform[k]) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  cert[e] = cert[e] & uniform_guess<T>(p, k, xv[u][k][e], jb[k][e]);
+                  okr[e] = okr[e] & (static_cast<unsigned>(jb[k][e]) < static_cast<unsigned>(p.nb[k]));
+                }
+              } else {
+                const T lo = Consts<T>::get(p, k, XHK_C_LO), hi = Consts<T>::get(p, k, XHK_C_HI), inv = lut_inv<T>(p, k);
+                const int G = p.lut_n[k], nb = p.nb[k], steps = p.lut_steps[k];
+                const unsigned short* lut = slut + p.lut_off[k];
+                const T* ed = sedges + p.eoff[k];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const T x = xv[u][k][e];
+                  okr[e] = okr[e] & (x >= lo) & (x <= hi);          // NaN: false
+                  int c = floor_to_int((x - lo) * inv);
+                  c = max(0, min(c, G - 1));
+                  jb[k][e] = static_cast<int>(lut[max(c - 1, 0)]);
+                }
+                for (int st = 0; st < steps; ++st) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int nx = min(jb[k][e] + 1, nb);
+                    jb[k][e] = (ed[nx] <= xv[u][k][e]) ? nx : jb[k][e];
+                  }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) jb[k][e] = min(jb[k][e], nb - 1);   // right-inclusive last bin
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              bool inwin = true; int wbin = 0, gbin = 0;
+#pragma unroll
+              for (int k = 0; k < KMAX; ++k) {
+                const unsigned jw = static_cast<unsigned>(jb[k][e] - wlo[k]);
+                inwin = inwin & (jw < static_cast<unsigned>(wlen[k]));
+                wbin = wbin * wlen[k] + static_cast<int>(jw);
+                gbin = gbin * p.nb[k] + jb[k][e];
+              }
+              const bool good = cert[e] & okr[e];
+              wb[u][e] = (good & inwin) ? wbin : -1;
+              if (good & !inwin) {                      // in range, outside the shared window: one global RED
+                if constexpr (W == 0) atomicAdd(out_row + gbin, 1ull);
+                else atomicAdd(out_row + gbin, static_cast<double>(wv[u][e]));
+              }
+              unsure |= (live & !cert[e]) ? (1u << (4 * u + e)) : 0u;
+            }
+          }
+          while (unsure) {   // rare: uncertain samples of uniform variables -> exact path
+            const int idx = __ffs(unsure) - 1;
+            unsure &= unsure - 1;
+            T x[KMAX]; WT wsel = WT(1);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (idx == 4 * u + e) {
+#pragma unroll
+                  for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
+                  wsel = wv[u][e];
+                }
+            const int wbin = general_sample(x, static_cast<double>(wsel), out_row);
+            if (wbin >= 0) shared_add1(wbin, wsel, out_row);
+          }
+        } else if constexpr (FAST) {
           // phase A (branch-free, U*4*K independent chains): guess, certainty, window test
           unsigned side = 0;   // bit (4u+e) set: that sample needs the side path
 #pragma unroll
@@ -700,26 +783,40 @@ __global__ void k_flush(uint4* buf, size_t n16) {
 // ---------------------------------------------------------------------------------------------
 typedef void (*HistKernel)(const XhkParams);
 
-template <typename T, int W>
-HistKernel pick_k(int K, bool fast) {
+template <typename T, int W, int MODE>
+HistKernel pick_k(int K) {
   switch (K) {
-    case 1: return fast ? k_hist<T, W, 1, true> : k_hist<T, W, 1, false>;
-    case 2: return fast ? k_hist<T, W, 2, true> : k_hist<T, W, 2, false>;
-    case 3: return fast ? k_hist<T, W, 3, true> : k_hist<T, W, 3, false>;
-    case 4: return fast ? k_hist<T, W, 4, true> : k_hist<T, W, 4, false>;
-    default: return k_hist<T, W, 0, false>;
+    case 1: return k_hist<T, W, 1, MODE>;
+    case 2: return k_hist<T, W, 2, MODE>;
+    case 3: return k_hist<T, W, 3, MODE>;
+    case 4: return k_hist<T, W, 4, MODE>;
+    default: return k_hist<T, W, 0, 0>;
   }
 }
+template <typename T, int W>
+HistKernel pick_m(int K, int mode) {
+  if (mode == 1) return pick_k<T, W, 1>(K);
+  if (mode == 2) return pick_k<T, W, 2>(K);
+  return pick_k<T, W, 0>(K);
+}
 
-HistKernel pick(int dtype, int w_dtype, int K, bool fast) {
+HistKernel pick(int dtype, int w_dtype, int K, int mode) {
   if (dtype == 1) {
-    if (w_dtype == 0) return pick_k<float, 0>(K, fast);
-    if (w_dtype == 1) return pick_k<float, 1>(K, fast);
-    return pick_k<float, 2>(K, fast);
+    if (w_dtype == 0) return pick_m<float, 0>(K, mode);
+    if (w_dtype == 1) return pick_m<float, 1>(K, mode);
+    return pick_m<float, 2>(K, mode);
   }
-  if (w_dtype == 0) return pick_k<double, 0>(K, fast);
-  if (w_dtype == 1) return pick_k<double, 1>(K, fast);
-  return pick_k<double, 2>(K, fast);
+  if (w_dtype == 0) return pick_m<double, 0>(K, mode);
+  if (w_dtype == 1) return pick_m<double, 1>(K, mode);
+  return pick_m<double, 2>(K, mode);
+}
+
+// Mode 2 keeps 4 samples x K variables of bins live; with 3+ fp64 variables that spills under the 64-register
+// budget and measured slower than the general kernel (config 5: 4.18 vs 3.93 ms), so it is used for small records only.
+int kernel_mode(const XhkParams& p, int dtype) {
+  if (p.all_uniform) return 1;
+  const int rec = p.n_vars * (dtype == 1 ? 4 : 8);
+  return (p.all_branch_free && rec <= 16) ? 2 : 0;
 }
 
 typedef void (*WindowKernel)(const XhkParams, XhkWindow*, int, int);
@@ -741,8 +838,8 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
   for (int dt = 1; dt <= 2; ++dt)
     for (int w = 0; w <= 2; ++w)
       for (int k = 1; k <= 5; ++k)
-        for (int f = 0; f <= 1; ++f) {
-          cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick(dt, w, k, f != 0)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+        for (int f = 0; f <= 2; ++f) {
+          cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick(dt, w, k, f)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
           if (e != cudaSuccess) return e;
         }
   // k_window has a little more static shared memory than k_hist
@@ -755,7 +852,7 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
 }
 
 cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l) {
-  HistKernel k = pick(l.dtype, l.w_dtype, p.n_vars, p.all_uniform != 0);
+  HistKernel k = pick(l.dtype, l.w_dtype, p.n_vars, kernel_mode(p, l.dtype));
   k<<<l.grid, l.threads, l.smem_bytes, l.stream>>>(p);
   return cudaGetLastError();
 }

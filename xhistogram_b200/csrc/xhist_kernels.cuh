@@ -52,6 +52,7 @@ struct XhkParams {
   int nb[XHK_MAX_VARS];             // bins of variable k  (= n_edges - 1)
   int uniform[XHK_MAX_VARS];        // 1: uniform fast path usable for variable k
   int all_uniform;                  // 1: every variable is uniform -> branch-free fast classification kernel
+  int all_branch_free;              // 1: every variable is uniform or has lut_steps > 0 -> branch-free mixed kernel
   int eoff[XHK_MAX_VARS];           // offset of variable k's effective edges in `edges`
   long long gmul[XHK_MAX_VARS];     // C-order multipliers of the global bin index
   const void* edges;                // device, typed T, all variables concatenated
@@ -61,6 +62,8 @@ struct XhkParams {
   const unsigned short* lut;        // device, all variables concatenated
   int n_lut_total;
   int lut_n[XHK_MAX_VARS];          // cells (0 = no table: plain binary search)
+  int lut_steps[XHK_MAX_VARS];      // > 0: at most this many edges lie within any 3 consecutive cells -> the bin is the
+                                    //      table entry of cell c-1 advanced by that many compare steps, no search loop
   int lut_off[XHK_MAX_VARS];
   float lut_invf[XHK_MAX_VARS];     // cells per unit of x, fp32 / fp64 kernels
   double lut_invd[XHK_MAX_VARS];

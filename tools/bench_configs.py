@@ -102,6 +102,16 @@ def main():
         for q in xs + [w]:
             q.free()
 
+    # many short rows (the typical `dim="depth"` reduction): 2e6 rows of 50 samples, 20 bins, with and without weights
+    M, N = max(1, int(2e6 * sc)), 50
+    x = DeviceArray.normal((M, N), np.float32, seed=21); w = DeviceArray.uniform((M, N), np.float32, seed=22)
+    e = np.linspace(-4, 4, 21)
+    _, best, med = timed([x], None, [e], [1], a.reps)
+    report("short rows 1xfp32 (2e6,50) 20 bins axis=-1", M * N, M * N * 4 + M * 20 * 8, best, med, "row-tiled")
+    _, best, med = timed([x], w, [e], [1], a.reps)
+    report("short rows weighted 1xfp32 (2e6,50) 20 bins axis=-1", M * N, M * N * 8 + M * 20 * 8, best, med, "row-tiled")
+    x.free(); w.free()
+
     with open(os.path.join(ROOT, "gpurun_out", "bench_configs.json"), "w") as f:
         json.dump(rows, f, indent=1)
 

@@ -313,9 +313,17 @@ int upload_edges(Ctx* c, const Prep& pr, cudaStream_t s) {
 }
 
 // Launch plan of one block whose data/weights/out pointers are DEVICE pointers.
-int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Plan& pl) {
+int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Plan& pl, int tile_rows = 1, long long tile_n = 0) {
   XhkParams& p = pl.p;
   p = pr.base;
+  p.tile_rows = tile_rows; p.tile_n = static_cast<int>(tile_n); p.tile_magic = 1; p.tile_shift = 0;
+  if (tile_rows > 1) {
+    // exact n / tile_n for n < 2^31: q = (umulhi(n, magic) + n) >> shift
+    int sh = 0; while ((1ll << sh) < tile_n) ++sh;
+    p.tile_shift = sh;
+    p.tile_magic = static_cast<unsigned>(((1ull << 32) * ((1ull << sh) - static_cast<unsigned long long>(tile_n))) / static_cast<unsigned long long>(tile_n) + 1ull);
+    p.B = pr.base.B * tile_rows;    // the launch addresses whole tiles: tile_rows rows of bins each
+  }
   const int K = d->n_vars;
   p.M = d->n_rows; p.N = d->n_cols;
   for (int k = 0; k < K; ++k) { p.data[k] = d->data[k]; p.stride[k] = d->row_stride[k]; }
@@ -436,7 +444,44 @@ int ensure_stage(Ctx* c, size_t bytes_per_slot) {
 }
 
 // device-resident block: everything on `stream`
+// Rows per tile for blocks of many short rows (1 = keep one row per segment).  A tile is handled like one long
+// row with tile_rows * B bins, so a CTA pays its barriers and its flush once per ~16K samples instead of once per
+// row, and the flush is one coalesced run of plain stores.
+int choose_tile_rows(Ctx* c, const Prep& pr, const xh_desc* d) {
+  const long long M = d->n_rows, N = d->n_cols, B = pr.base.B;
+  if (M < 2 || N < 1 || N >= 8192 || (d->flags & (XH_FLAG_FORCE_GLOBAL | XH_FLAG_FORCE_WINDOW | XH_FLAG_NO_ZERO))) return 1;
+  for (int k = 0; k < d->n_vars; ++k) if (d->row_stride[k] != N) return 1;   // contiguous rows only
+  if (d->weights && d->w_row_stride != N) return 1;
+  const long long item = d->w_dtype == XH_NONE ? 4 : 8;
+  const long long per_cta = (static_cast<long long>(c->smem_per_sm) / 2 - 1024 - 64 - static_cast<long long>(pr.edges_al)) / item - 32;
+  const long long r_max = std::min<long long>(per_cta / std::max<long long>(B, 1), M);
+  const long long target = 16384;
+  long long R = std::min<long long>(r_max, (target + N - 1) / N);
+  R = std::min<long long>(R, ((1ll << 30) - 1) / N);
+  return R >= 2 ? static_cast<int>(R) : 1;
+}
+
 int run_device_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream) {
+  const int R = choose_tile_rows(c, pr, d);
+  if (R > 1) {
+    const long long M = d->n_rows, N = d->n_cols, tiles = M / R, rem = M % R;
+    const size_t tsz = dsize(d->dtype), wsz = dsize(d->w_dtype);
+    xh_desc t = *d;
+    t.n_rows = tiles; t.n_cols = static_cast<long long>(R) * N;
+    for (int k = 0; k < d->n_vars; ++k) t.row_stride[k] = t.n_cols;
+    if (d->weights) t.w_row_stride = t.n_cols;
+    Plan pl;
+    int rc = plan_block(c, pr, &t, stream, pl, R, N);
+    if (rc) return rc;
+    rc = enqueue(c, pr, pl);
+    if (rc || rem == 0) return rc;
+    xh_desc r = *d;                                  // the last M % R rows
+    r.n_rows = rem;
+    for (int k = 0; k < d->n_vars; ++k) r.data[k] = static_cast<const unsigned char*>(d->data[k]) + static_cast<size_t>(tiles) * R * N * tsz;
+    if (d->weights) r.weights = static_cast<const unsigned char*>(d->weights) + static_cast<size_t>(tiles) * R * N * wsz;
+    r.out = static_cast<unsigned char*>(d->out) + static_cast<size_t>(tiles) * R * pr.base.B * 8;
+    return run_device_block(c, pr, &r, stream);
+  }
   Plan pl;
   int rc = plan_block(c, pr, d, stream, pl);
   if (rc) return rc;

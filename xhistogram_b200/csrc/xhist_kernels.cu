@@ -178,6 +178,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   for (int k = 0; k < KMAX; ++k) {
     if (k < K) { wlo[k] = s_wlo[k]; wlen[k] = s_wlen[k]; wtot *= wlen[k]; } else { wlo[k] = 0; wlen[k] = 0; }
   }
+  // row tiling: the shared histogram holds tile_rows rows; a sample's bin is offset by (local row) * (bins per row),
+  // obtained for free by seeding the Horner evaluation of the joint bin with the local row
+  const bool tiled = p.tile_rows > 1;
+  wtot *= p.tile_rows;
   for (int i = tid; i < (W == 0 ? wtot : wtot + 32); i += nthr) shist[i] = HT(0);
   // weighted accumulation mode (uniform for the launch): exact fixed point in two u32 limbs, or float64 adds
   bool fx = false; WT fx_mul = WT(0), fx_limit = WT(0); double fx_unmul = 0.0;
@@ -211,8 +215,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   };
   // general path of one sample: exact bins, then shared window / global spill / drop.
   // Returns the window bin when the caller should do the shared add itself, else -1.
-  auto general_sample = [&](const T (&x)[KMAX], double wv, OT* out_row) -> int {
-    int j[KMAX]; int wbin = 0; bool ok = true, inwin = true;
+  auto general_sample = [&](const T (&x)[KMAX], double wv, OT* out_row, int rowl) -> int {
+    int j[KMAX]; int wbin = rowl; bool ok = true, inwin = true;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k < K) {
@@ -234,6 +238,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   };
   // window bin -> global bin (rare paths only)
   auto window_to_global = [&](int wbin) -> long long {
+    if (p.hist_mode == XHK_FULL) return wbin;     // the window is the whole (possibly tiled) bin space
     int rem = wbin; long long gbin = 0;
 #pragma unroll
     for (int k = KMAX - 1; k >= 0; --k) {
@@ -300,6 +305,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
     const long long nvec = (len - head) >> 2;  // groups of 4 samples
     const long long tail0 = head + (nvec << 2);
 
+    // local row of sample i of this segment inside its tile (0 without tiling)
+    auto local_row = [&](long long i) -> int {
+      if (!tiled) return 0;
+      const unsigned n = static_cast<unsigned>(c0 + i);
+      return static_cast<int>((__umulhi(n, p.tile_magic) + n) >> p.tile_shift);
+    };
     // scalar head and tail (and everything when the arrays are not mutually 16-byte alignable)
     auto scalar_at = [&](long long i) {
       T x[KMAX];
@@ -307,7 +318,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       for (int k = 0; k < KMAX; ++k) x[k] = (k < K) ? px[k][i] : T(0);
       WT wv[4] = {WT(1), WT(1), WT(1), WT(1)};
       if constexpr (W != 0) wv[0] = pw[i];
-      const int wbin = general_sample(x, static_cast<double>(wv[0]), out_row);
+      const int wbin = general_sample(x, static_cast<double>(wv[0]), out_row, local_row(i));
       if (wbin >= 0) shared_add1(wbin, wv[0], out_row);
     };
     for (long long i = tid; i < head; i += nthr) scalar_at(i);
@@ -376,7 +387,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              bool inwin = true; int wbin = 0, gbin = 0;
+              bool inwin = true; int wbin = local_row(head + 4 * (g + static_cast<long long>(u) * nthr) + e), gbin = 0;
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) {
                 const unsigned jw = static_cast<unsigned>(jb[k][e] - wlo[k]);
@@ -406,7 +417,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
                   for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
                   wsel = wv[u][e];
                 }
-            const int wbin = general_sample(x, static_cast<double>(wsel), out_row);
+            const int wbin = general_sample(x, static_cast<double>(wsel), out_row,
+                                            local_row(head + 4 * (g + static_cast<long long>(idx >> 2) * nthr) + (idx & 3)));
             if (wbin >= 0) shared_add1(wbin, wsel, out_row);
           }
         } else if constexpr (FAST) {
@@ -417,7 +429,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             const bool live = g + static_cast<long long>(u) * nthr < nvec;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              bool good = true; int wbin = 0;
+              bool good = true; int wbin = local_row(head + 4 * (g + static_cast<long long>(u) * nthr) + e);
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) {
                 int j;
@@ -452,9 +464,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
               sure = sure & certain & (static_cast<unsigned>(jx) < static_cast<unsigned>(p.nb[k]));
               gbin = gbin * p.nb[k] + jx;
             }
-            if (sure) global_add(out_row, gbin, static_cast<double>(wsel));
+            if (sure && !tiled) global_add(out_row, gbin, static_cast<double>(wsel));   // (tiling implies a full window)
             else {
-              const int wbin = general_sample(x, static_cast<double>(wsel), out_row);
+              const int wbin = general_sample(x, static_cast<double>(wsel), out_row,
+                                              local_row(head + 4 * (g + static_cast<long long>(idx >> 2) * nthr) + (idx & 3)));
               if (wbin >= 0) shared_add1(wbin, wsel, out_row);
             }
           }
@@ -467,7 +480,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
               T x[KMAX];
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
-              wb[u][e] = live ? general_sample(x, static_cast<double>(wv[u][e]), out_row) : -1;
+              wb[u][e] = live ? general_sample(x, static_cast<double>(wv[u][e]), out_row, local_row(head + 4 * (g + static_cast<long long>(u) * nthr) + e)) : -1;
             }
           }
         }

@@ -80,6 +80,11 @@ struct XhkParams {
   int wlen[XHK_MAX_VARS];
   long long per_cta;                // XHK_PART_SAMPLES: samples per CTA (multiple of 1024)
   int w_dtype;                      // 0 none, 1 fp32, 2 fp64 (for the probe kernel)
+  // row tiling (many short rows): the launch sees tile_rows consecutive rows as one row of N = tile_rows*tile_n
+  // samples and B = tile_rows * prod(nb) bins; the local row of a sample is (offset in the tile) / tile_n
+  int tile_rows;                    // 1 = no tiling
+  int tile_n;                       // samples of one real row
+  unsigned tile_magic; int tile_shift;   // q = (umulhi(n, magic) + n) >> shift == n / tile_n for n < 2^31
   int fx_vbits;                     // fixed point: |v| < 2^fx_vbits keeps every per-flush bin sum below 2^63
 };
 

@@ -42,7 +42,7 @@ typedef enum xh_status {
   XH_ERR_UNSUPPORTED = -6  /* valid request this build does not implement       */
 } xh_status;
 
-typedef enum xh_dtype { XH_NONE = 0, XH_F32 = 1, XH_F64 = 2 } xh_dtype;
+typedef enum xh_dtype { XH_NONE = 0, XH_F32 = 1, XH_F64 = 2, XH_I64 = 3 /* data only: int64, datetime64/timedelta64 ticks */ } xh_dtype;
 typedef enum xh_mem { XH_HOST = 0, XH_DEVICE = 1 } xh_mem;
 
 /* flags for xh_desc.flags */
@@ -63,7 +63,8 @@ typedef enum xh_mem { XH_HOST = 0, XH_DEVICE = 1 } xh_mem;
  *                row_stride 0 broadcasts one row over all rows (core.py:366).
  *   weights      optional, same addressing with w_row_stride; any weights make the
  *                result float64 accumulated in float64 (np.bincount, core.py:81).
- *   edges[k]     HOST float64, n_edges[k] >= 2 non-decreasing values; comparison
+ *   edges[k]     HOST float64 (int64 in iedges[k] when dtype == XH_I64: integers and datetime64 ticks compare
+ *                exactly, as numpy compares them), n_edges[k] >= 2 non-decreasing values; comparison
  *                semantics are numpy's (data promoted with the edges; fp32 data
  *                against fp32-representable edges compares in fp32 — identical
  *                results).
@@ -90,6 +91,7 @@ typedef struct xh_desc {
   void* out;
   void* stream;                       /* cudaStream_t for device inputs; NULL = library stream */
   float* kernel_ms;                   /* optional: device time of the kernels of this call   */
+  const int64_t* iedges[XH_MAX_VARS]; /* dtype == XH_I64: the edges as int64 (edges[] unused)  */
 } xh_desc;
 
 /* library / device lifecycle --------------------------------------------------------- */

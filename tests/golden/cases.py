@@ -272,3 +272,45 @@ def log_spaced_edges_f32():
     r = _rng(29)
     x = np.exp(r.uniform(-9, 9, 6000)).astype(np.float32)
     return [x], dict(bins=np.logspace(-3, 3, 37))
+
+
+# ---------------------------------------------------------------- exact integer path (int64 kernel)
+@case
+def datetime_ns_data_day_edges():                 # test_core.py:365-382 (datetime64 data and edges of different units)
+    data = np.arange("2000-06-01", "2000-06-06", dtype="datetime64[D]").astype("datetime64[ns]")
+    bins = np.array(["1999-01-01", "2000-01-01", "2001-01-01"], dtype="datetime64[D]")
+    return [data], dict(bins=bins)
+
+
+@case
+def datetime_rows_with_nat():
+    r = _rng(30)
+    base = np.datetime64("2001-01-01T00:00:00", "s")
+    data = (base + r.integers(-400 * 86400, 400 * 86400, (6, 500)).astype("timedelta64[s]"))
+    data[2, 5] = np.datetime64("NaT")
+    bins = np.arange("2000-01-01", "2002-02-01", dtype="datetime64[M]")
+    return [data], dict(bins=bins, axis=1)
+
+
+@case
+def timedelta_flat():
+    r = _rng(31)
+    data = r.integers(-50, 150, 2000).astype("timedelta64[h]")
+    return [data], dict(bins=np.arange(0, 101, 10).astype("timedelta64[h]"))
+
+
+@case
+def int64_beyond_2_53_integer_edges():            # not representable in float64: compared as integers
+    r = _rng(32)
+    big = 2**60
+    data = big + r.integers(-1000, 1000, 3000)
+    bins = big + np.arange(-1000, 1001, 100)
+    return [data], dict(bins=bins)
+
+
+@case
+def int32_joint_integer_edges_weighted():
+    r = _rng(33)
+    a = r.integers(0, 50, (4, 800)).astype(np.int32)
+    b = r.integers(-20, 20, (4, 800)).astype(np.int16)
+    return [a, b], dict(bins=[np.arange(0, 51, 5), np.arange(-20, 21, 4)], axis=1, weights=r.random((4, 800)))

@@ -22,10 +22,17 @@ def _oracle_desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem,
         assert stride == N and a.shape[0] == M
         return a
     data = [full(a, s) for a, s in zip(arrs, strides)]
-    assert all(a.dtype == data[0].dtype for a in data) and data[0].dtype in (np.float32, np.float64)
+    assert all(a.dtype == data[0].dtype for a in data)
+    from xhistogram_b200 import _cabi
+    if dtype == _cabi.XH_I64:
+        assert data[0].dtype == np.int64 and all(np.asarray(b).dtype == np.int64 for b in bins)
+        edges = [np.asarray(b) for b in bins]
+    else:
+        assert data[0].dtype == {_cabi.XH_F32: np.float32, _cabi.XH_F64: np.float64}[dtype]
+        edges = [np.asarray(b, dtype=np.float64) for b in bins]
     ww = None if w is None else full(w, wstride)
     B = int(np.prod([len(b) - 1 for b in bins]))
-    return O.block_bincount(data, [np.asarray(b, dtype=np.float64) for b in bins], ww).reshape(M, B)
+    return O.block_bincount(data, edges, ww).reshape(M, B)
 
 
 @pytest.fixture
@@ -133,8 +140,10 @@ def test_errors(patched):
         core.histogram(x, bins="auto", weights=np.ones_like(x))         # numpy: estimators do not take weights
     with pytest.raises(ValueError):
         core.histogram(x, bins=np.array([0.0, 2.0, 1.0]))               # edges must increase
+    with pytest.raises(TypeError):                                      # datetime data needs datetime edges
+        core.histogram(np.array(["2000-01-01"], dtype="datetime64[D]"), bins=np.array([0.0, 1.0]))
     with pytest.raises(TypeError):
-        core.histogram(np.array(["2000-01-01"], dtype="datetime64[D]"), bins=np.array(["1999-01-01", "2001-01-01"], dtype="datetime64[D]"))
+        core.histogram(np.array([1 + 2j]), bins=np.array([0.0, 2.0]))
 
 
 def test_integer_and_bool_data(patched):
@@ -146,4 +155,5 @@ def test_integer_and_bool_data(patched):
     assert np.array_equal(core.histogram(xb, bins=2, range=(0, 1))[0], np.histogram(xb, bins=2, range=(0, 1))[0])
     big = np.array([2**60 + 1], dtype=np.int64)
     with pytest.raises(TypeError):
-        core.histogram(big, bins=np.array([0.0, 2.0**61]))
+        core.histogram(big, bins=np.array([0.0, 2.0**61]))             # float edges: the float64 cast would be lossy
+    assert core.histogram(big, bins=np.array([0, 2**61]))[0].tolist() == [1]   # integer edges: exact int64 path

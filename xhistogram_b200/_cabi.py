@@ -12,7 +12,7 @@ import os
 import threading
 
 XH_MAX_VARS = 8
-XH_NONE, XH_F32, XH_F64 = 0, 1, 2
+XH_NONE, XH_F32, XH_F64, XH_I64 = 0, 1, 2, 3
 XH_HOST, XH_DEVICE = 0, 1
 XH_FLAG_NO_ZERO = 1
 XH_FLAG_FORCE_GLOBAL = 2
@@ -53,6 +53,7 @@ class XhDesc(C.Structure):
         ("out", C.c_void_p),
         ("stream", C.c_void_p),
         ("kernel_ms", C.POINTER(C.c_float)),
+        ("iedges", C.POINTER(C.c_int64) * XH_MAX_VARS),
     ]
 
 

@@ -75,8 +75,9 @@ def _as_float_data(a):
 
     numpy promotes data and float edges to a common float type before searchsorted; float16 and
     integers up to 32 bits are exact in that type.  64-bit integers are accepted when the cast to
-    float64 is lossless for this array; anything else (datetime64, complex, object) is refused —
-    there is no CPU fallback to hide it.
+    float64 is lossless for this array (integer data with integer edges and datetime64/timedelta64 take the
+    exact int64 path instead, see ``_int64_plan``); anything else (complex, object) is refused — there is no
+    CPU fallback to hide it.
     """
     dt = a.dtype
     if dt == np.float32 or dt == np.float64:
@@ -93,6 +94,42 @@ def _as_float_data(a):
     if dt.kind == "f":  # longdouble
         return a.astype(np.float64)
     raise TypeError(f"unsupported data dtype {dt} for the B200 histogram path (float and integer data only)")
+
+
+def _int64_plan(data, bins):
+    """Exact integer path: datetime64/timedelta64 data, or integer data with integer edges.
+
+    numpy compares such data and edges as integers (datetimes after conversion to their common unit), so
+    they are handed to the int64 kernel as ticks.  NaT (the most negative int64) sorts last in numpy, i.e. it
+    is never counted; as an integer it is below every edge, so it is dropped as well.
+    Returns ``(int64 arrays, int64 edges)`` or ``None`` when the float path applies.
+    """
+    kinds = {a.dtype.kind for a in data}
+    ekinds = {np.asarray(b).dtype.kind for b in bins}
+    if kinds & set("mM") or ekinds & set("mM"):
+        if len(kinds) != 1 or kinds != ekinds:
+            raise TypeError("datetime64/timedelta64 data needs bin edges of the same kind for every argument")
+        arrs, edges = [], []
+        for a, b in zip(data, bins):
+            b = np.asarray(b)
+            common = np.result_type(a.dtype, b.dtype)
+            arrs.append(a.astype(common).view(np.int64))
+            edges.append(b.astype(common).view(np.int64))
+        return arrs, edges
+    if kinds <= set("iub") and ekinds <= set("iu"):
+        arrs = []
+        for a in data:
+            if a.dtype == np.uint64 and a.size and int(a.max()) > np.iinfo(np.int64).max:
+                raise TypeError("uint64 data above 2**63-1 is not supported")
+            arrs.append(a.astype(np.int64, copy=False))
+        edges = []
+        for b in bins:
+            b = np.asarray(b)
+            if b.dtype == np.uint64 and b.size and int(b.max()) > np.iinfo(np.int64).max:
+                raise TypeError("uint64 edges above 2**63-1 are not supported")
+            edges.append(b.astype(np.int64))
+        return arrs, edges
+    return None
 
 
 def _as_float_weights(w):
@@ -237,16 +274,21 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
             return out                                       # DeviceArray (M * prod(bins)), stays in HBM
         return out.reshape(kept_axes_shape + nbins)
 
-    data = [_as_float_data(np.asarray(a)) for a in all_arrays]
-    if len({a.dtype for a in data}) > 1:
-        data = [a.astype(np.float64) for a in data]   # exact: float32 -> float64 (numpy promotes the same way)
+    raw = [np.asarray(a) for a in all_arrays]
+    iplan = _int64_plan(raw, bins)
+    if iplan is not None:
+        data, bins = iplan
+    else:
+        data = [_as_float_data(a) for a in raw]
+        if len({a.dtype for a in data}) > 1:
+            data = [a.astype(np.float64) for a in data]   # exact: float32 -> float64 (numpy promotes the same way)
     if w is not None:
         w = _as_float_weights(np.asarray(w))
     ax = None if full else list(axis)
     rows = [_rows_view(a, ax, full) for a in data]
     M, N = rows[0][2], rows[0][3]
     wrow = _rows_view(w, ax, full) if w is not None else None
-    xdt = _xh_dtype(data[0].dtype)
+    xdt = _cabi.XH_I64 if iplan is not None else _xh_dtype(data[0].dtype)
     out = _host_call([r[0] for r in rows], [r[1] for r in rows], wrow, bins, M, N, xdt, _devices, _flags, _timing)
     return out.reshape(kept_axes_shape + nbins)
 
@@ -280,9 +322,13 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
         else:
             d.data[k] = arrs[k]
         d.row_stride[k] = strides[k]
-        e = np.ascontiguousarray(bins[k], dtype=np.float64)
+        if dtype == _cabi.XH_I64:
+            e = np.ascontiguousarray(bins[k], dtype=np.int64)
+            d.iedges[k] = e.ctypes.data_as(C.POINTER(C.c_int64))
+        else:
+            e = np.ascontiguousarray(bins[k], dtype=np.float64)
+            d.edges[k] = e.ctypes.data_as(C.POINTER(C.c_double))
         keep.append(e)
-        d.edges[k] = e.ctypes.data_as(C.POINTER(C.c_double))
         d.n_edges[k] = e.size
     if w is not None:
         d.weights = (w.ctypes.data if w.size else None) if mem == _cabi.XH_HOST else w
@@ -385,7 +431,7 @@ def histogram(*args, bins=None, range=None, axis=None, weights=None, density=Fal
         bins = [_resolve_edges(a, b, r, w_for_edges) for a, b, r in zip(all_arrays, bins, range)]
 
     for b in bins:
-        if np.asarray(b).dtype.kind not in "fiu":
+        if np.asarray(b).dtype.kind not in "fiumM":
             raise TypeError(f"unsupported bin-edge dtype {np.asarray(b).dtype} for the B200 histogram path")
 
     drop_axes = tuple(axis) if axis is not None else input_axes

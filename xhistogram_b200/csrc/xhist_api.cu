@@ -40,7 +40,7 @@ int fail(int code, const char* fmt, ...) {
                   cudaGetErrorString(e__), __FILE__, __LINE__);                                      \
   } while (0)
 
-size_t dsize(int dt) { return dt == XH_F32 ? 4 : dt == XH_F64 ? 8 : 0; }
+size_t dsize(int dt) { return dt == XH_F32 ? 4 : (dt == XH_F64 || dt == XH_I64) ? 8 : 0; }
 
 // ------------------------------------------------------------------------------------------ NCCL (dlopen)
 struct Id128 { char b[XH_NCCL_UNIQUE_ID_BYTES]; };
@@ -239,6 +239,17 @@ int prep_var(const double* e, int E, int k, bool force_search, XhkParams& p, std
   return XH_OK;
 }
 
+// int64 data (integers, datetime64/timedelta64 ticks): exact integer compares, binary search only
+int prep_var_i64(const int64_t* e, int E, int k, XhkParams& p, std::vector<long long>& table) {
+  for (int j = 1; j < E; ++j) if (e[j] < e[j - 1]) return fail(XH_ERR_INVALID, "edges of variable %d must increase monotonically", k);
+  p.nb[k] = E - 1;
+  p.eoff[k] = static_cast<int>(table.size());
+  for (int j = 0; j < E; ++j) table.push_back(e[j]);
+  p.ci[k][XHK_C_LO] = e[0]; p.ci[k][XHK_C_HI] = e[E - 1];
+  p.uniform[k] = 0; p.lut_n[k] = 0; p.lut_steps[k] = 0; p.lut_off[k] = 0;
+  return XH_OK;
+}
+
 // ------------------------------------------------------------------------------------------ plan + launch
 struct Plan {
   XhkParams p;
@@ -265,10 +276,11 @@ int prep_call(const xh_desc* d, Prep& pr) {
   const size_t tsz = dsize(d->dtype);
   p.n_vars = K;
   const bool force_search = (d->flags & XH_FLAG_FORCE_SEARCH) != 0;
-  std::vector<float> tf; std::vector<double> td;
+  std::vector<float> tf; std::vector<double> td; std::vector<long long> ti;
   for (int k = 0; k < K; ++k) {
-    int rc = (d->dtype == XH_F32) ? prep_var<float>(d->edges[k], d->n_edges[k], k, force_search, p, tf)
-                                  : prep_var<double>(d->edges[k], d->n_edges[k], k, force_search, p, td);
+    int rc = (d->dtype == XH_I64) ? prep_var_i64(d->iedges[k], d->n_edges[k], k, p, ti)
+             : (d->dtype == XH_F32) ? prep_var<float>(d->edges[k], d->n_edges[k], k, force_search, p, tf)
+                                    : prep_var<double>(d->edges[k], d->n_edges[k], k, force_search, p, td);
     if (rc) return rc;
   }
   long long B = 1;
@@ -281,11 +293,11 @@ int prep_call(const xh_desc* d, Prep& pr) {
   for (int k = 0; k < K; ++k) p.all_uniform = p.all_uniform && p.uniform[k];
   long long mul = 1;
   for (int k = K - 1; k >= 0; --k) { p.gmul[k] = mul; mul *= p.nb[k]; }
-  p.n_edges_total = static_cast<int>(d->dtype == XH_F32 ? tf.size() : td.size());
+  p.n_edges_total = static_cast<int>(d->dtype == XH_F32 ? tf.size() : d->dtype == XH_F64 ? td.size() : ti.size());
   const size_t edge_bytes = p.n_edges_total * tsz;
   std::vector<unsigned short> lut;
   for (int k = 0; k < K; ++k) {
-    if (d->flags & XH_FLAG_FORCE_SEARCH) { p.lut_n[k] = 0; p.lut_off[k] = 0; p.lut_steps[k] = 0; continue; }
+    if ((d->flags & XH_FLAG_FORCE_SEARCH) || d->dtype == XH_I64) { p.lut_n[k] = 0; p.lut_off[k] = 0; p.lut_steps[k] = 0; continue; }
     if (d->dtype == XH_F32) build_lut<float>(k, p, tf, lut); else build_lut<double>(k, p, td, lut);
   }
   p.n_lut_total = static_cast<int>(lut.size());
@@ -293,7 +305,8 @@ int prep_call(const xh_desc* d, Prep& pr) {
   for (int k = 0; k < K; ++k) p.all_branch_free = p.all_branch_free && (p.uniform[k] || p.lut_steps[k] > 0);
   pr.lut_dev_off = (edge_bytes + 15) & ~static_cast<size_t>(15);
   pr.edge_host.assign(pr.lut_dev_off + lut.size() * 2, 0);
-  std::memcpy(pr.edge_host.data(), d->dtype == XH_F32 ? static_cast<const void*>(tf.data()) : static_cast<const void*>(td.data()), edge_bytes);
+  std::memcpy(pr.edge_host.data(), d->dtype == XH_F32 ? static_cast<const void*>(tf.data())
+                                   : d->dtype == XH_F64 ? static_cast<const void*>(td.data()) : static_cast<const void*>(ti.data()), edge_bytes);
   if (!lut.empty()) std::memcpy(pr.edge_host.data() + pr.lut_dev_off, lut.data(), lut.size() * 2);
   pr.edges_al = pr.lut_dev_off + ((lut.size() * 2 + 15) & ~static_cast<size_t>(15));
   return XH_OK;
@@ -416,13 +429,14 @@ int enqueue(Ctx* c, const Prep& pr, Plan& pl) {
 int validate(const xh_desc* d) {
   if (!d) return fail(XH_ERR_INVALID, "null descriptor");
   if (d->n_vars < 1 || d->n_vars > XH_MAX_VARS) return fail(XH_ERR_INVALID, "n_vars must be 1..%d", XH_MAX_VARS);
-  if (d->dtype != XH_F32 && d->dtype != XH_F64) return fail(XH_ERR_INVALID, "dtype must be XH_F32 or XH_F64");
+  if (d->dtype != XH_F32 && d->dtype != XH_F64 && d->dtype != XH_I64) return fail(XH_ERR_INVALID, "dtype must be XH_F32, XH_F64 or XH_I64");
   if (d->w_dtype != XH_NONE && d->w_dtype != XH_F32 && d->w_dtype != XH_F64) return fail(XH_ERR_INVALID, "bad w_dtype");
   if ((d->w_dtype != XH_NONE) != (d->weights != nullptr)) return fail(XH_ERR_INVALID, "weights pointer and w_dtype disagree");
   if (d->n_rows < 0 || d->n_cols < 0) return fail(XH_ERR_INVALID, "negative shape");
   if (!d->out) return fail(XH_ERR_INVALID, "out is null");
   for (int k = 0; k < d->n_vars; ++k) {
-    if (!d->edges[k] || d->n_edges[k] < 2) return fail(XH_ERR_INVALID, "variable %d needs at least 2 edges", k);
+    if (!(d->dtype == XH_I64 ? static_cast<const void*>(d->iedges[k]) : static_cast<const void*>(d->edges[k])) || d->n_edges[k] < 2)
+      return fail(XH_ERR_INVALID, "variable %d needs at least 2 edges", k);
     if (d->n_rows > 0 && d->n_cols > 0 && !d->data[k]) return fail(XH_ERR_INVALID, "data[%d] is null", k);
     if (d->row_stride[k] < 0) return fail(XH_ERR_INVALID, "negative row stride");
     if (reinterpret_cast<uintptr_t>(d->data[k]) % dsize(d->dtype)) return fail(XH_ERR_INVALID, "data[%d] is not element-aligned", k);

@@ -27,9 +27,13 @@ template <> struct Consts<float> {
 template <> struct Consts<double> {
   static __device__ __forceinline__ double get(const XhkParams& p, int k, int i) { return p.cd[k][i]; }
 };
+template <> struct Consts<long long> {   // int64 data (integers, datetime64 ticks): range limits only
+  static __device__ __forceinline__ long long get(const XhkParams& p, int k, int i) { return i < 2 ? p.ci[k][i] : 0ll; }
+};
 
 __device__ __forceinline__ int floor_to_int(float t) { return __float2int_rd(t); }
 __device__ __forceinline__ int floor_to_int(double t) { return __double2int_rd(t); }
+__device__ __forceinline__ int floor_to_int(long long t) { return static_cast<int>(t); }   // never used (no uniform / table path for int64)
 
 // shared-memory atomics on explicit 32-bit shared addresses (no generic->shared conversion per use)
 __device__ __forceinline__ void reds_add_u32(unsigned addr, unsigned v) {
@@ -80,6 +84,7 @@ __device__ __forceinline__ bool uniform_guess(const XhkParams& p, int k, T x, in
 template <typename T> __device__ __forceinline__ T lut_inv(const XhkParams& p, int k);
 template <> __device__ __forceinline__ float lut_inv<float>(const XhkParams& p, int k) { return p.lut_invf[k]; }
 template <> __device__ __forceinline__ double lut_inv<double>(const XhkParams& p, int k) { return p.lut_invd[k]; }
+template <> __device__ __forceinline__ long long lut_inv<long long>(const XhkParams&, int) { return 0ll; }
 
 // Non-uniform edges: the cell of x in a uniform partition of [lo, hi] brackets #{e_j <= x} between the table
 // entries of cell c-1 and cell c+2 (one cell of slack on either side absorbs the rounding of the cell index),
@@ -124,6 +129,11 @@ __device__ __noinline__ int exact_bin(const XhkParams& p, int k, const T* __rest
 __device__ __forceinline__ void load4(const float* p, long long g, float (&v)[4]) {
   float4 q = __ldcs(reinterpret_cast<const float4*>(p) + g);
   v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+__device__ __forceinline__ void load4(const long long* p, long long g, long long (&v)[4]) {
+  longlong2 a = __ldcs(reinterpret_cast<const longlong2*>(p) + 2 * g);
+  longlong2 b = __ldcs(reinterpret_cast<const longlong2*>(p) + 2 * g + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 __device__ __forceinline__ void load4(const double* p, long long g, double (&v)[4]) {
   double2 a = __ldcs(reinterpret_cast<const double2*>(p) + 2 * g);
@@ -814,6 +824,11 @@ HistKernel pick_m(int K, int mode) {
 }
 
 HistKernel pick(int dtype, int w_dtype, int K, int mode) {
+  if (dtype == 3) {   // int64 data: general kernel only
+    if (w_dtype == 0) return pick_k<long long, 0, 0>(K);
+    if (w_dtype == 1) return pick_k<long long, 1, 0>(K);
+    return pick_k<long long, 2, 0>(K);
+  }
   if (dtype == 1) {
     if (w_dtype == 0) return pick_m<float, 0>(K, mode);
     if (w_dtype == 1) return pick_m<float, 1>(K, mode);
@@ -827,6 +842,7 @@ HistKernel pick(int dtype, int w_dtype, int K, int mode) {
 // Mode 2 keeps 4 samples x K variables of bins live; with 3+ fp64 variables that spills under the 64-register
 // budget and measured slower than the general kernel (config 5: 4.18 vs 3.93 ms), so it is used for small records only.
 int kernel_mode(const XhkParams& p, int dtype) {
+  if (dtype == 3) return 0;
   if (p.all_uniform) return 1;
   const int rec = p.n_vars * (dtype == 1 ? 4 : 8);
   return (p.all_branch_free && rec <= 16) ? 2 : 0;
@@ -843,12 +859,14 @@ WindowKernel pick_window_t(int K) {
     default: return k_window<T, 0>;
   }
 }
-WindowKernel pick_window(int dtype, int K) { return dtype == 1 ? pick_window_t<float>(K) : pick_window_t<double>(K); }
+WindowKernel pick_window(int dtype, int K) {
+  return dtype == 1 ? pick_window_t<float>(K) : dtype == 2 ? pick_window_t<double>(K) : pick_window_t<long long>(K);
+}
 
 }  // namespace
 
 cudaError_t xhk_set_smem_limits(int max_optin) {
-  for (int dt = 1; dt <= 2; ++dt)
+  for (int dt = 1; dt <= 3; ++dt)
     for (int w = 0; w <= 2; ++w)
       for (int k = 1; k <= 5; ++k)
         for (int f = 0; f <= 2; ++f) {
@@ -856,7 +874,7 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
           if (e != cudaSuccess) return e;
         }
   // k_window has a little more static shared memory than k_hist
-  for (int dt = 1; dt <= 2; ++dt)
+  for (int dt = 1; dt <= 3; ++dt)
     for (int k = 0; k <= 4; ++k) {
       cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_window(dt, k)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 192);
       if (e != cudaSuccess) return e;

@@ -49,6 +49,7 @@ struct XhkParams {
   //   [XHK_C_DELTA],[XHK_C_OMD] uniform path: bin certain iff delta <= frac(t) <= omd
   float cf[XHK_MAX_VARS][6];
   double cd[XHK_MAX_VARS][6];
+  long long ci[XHK_MAX_VARS][2];    // int64 kernels: [XHK_C_LO], [XHK_C_HI] only (no uniform path)
   int nb[XHK_MAX_VARS];             // bins of variable k  (= n_edges - 1)
   int uniform[XHK_MAX_VARS];        // 1: uniform fast path usable for variable k
   int all_uniform;                  // 1: every variable is uniform -> branch-free fast classification kernel
@@ -89,7 +90,7 @@ struct XhkParams {
 };
 
 struct XhkLaunch {
-  int dtype;       // 1 f32, 2 f64 (xh_dtype)
+  int dtype;       // 1 f32, 2 f64, 3 int64 (xh_dtype)
   int w_dtype;     // 0 none, 1 f32, 2 f64
   int grid, threads;
   size_t smem_bytes;

@@ -68,6 +68,10 @@ typedef enum xh_mem { XH_HOST = 0, XH_DEVICE = 1 } xh_mem;
  *                semantics are numpy's (data promoted with the edges; fp32 data
  *                against fp32-representable edges compares in fp32 — identical
  *                results).
+ *   n_inner      column layout for reductions over LEADING axes (np.moveaxis + reshape in core.py:218-226 would
+ *                copy): the arrays are C-contiguous (n_outer, n_cols, n_inner) blocks, n_rows = n_outer*n_inner,
+ *                logical row a*n_inner + m holds the samples data[k][(a*n_cols + c)*n_inner + m], c < n_cols;
+ *                row strides are ignored.
  *   out          (n_rows, prod(n_edges[k]-1)) C-order; int64 without weights,
  *                float64 with weights; caller-owned, library zero-fills unless
  *                XH_FLAG_NO_ZERO.
@@ -92,6 +96,7 @@ typedef struct xh_desc {
   void* stream;                       /* cudaStream_t for device inputs; NULL = library stream */
   float* kernel_ms;                   /* optional: device time of the kernels of this call   */
   const int64_t* iedges[XH_MAX_VARS]; /* dtype == XH_I64: the edges as int64 (edges[] unused)  */
+  int64_t n_inner;                    /* > 1: column layout (reduced axes lead, see below); 0/1: row layout */
 } xh_desc;
 
 /* library / device lifecycle --------------------------------------------------------- */

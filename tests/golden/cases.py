@@ -314,3 +314,25 @@ def int32_joint_integer_edges_weighted():
     a = r.integers(0, 50, (4, 800)).astype(np.int32)
     b = r.integers(-20, 20, (4, 800)).astype(np.int16)
     return [a, b], dict(bins=[np.arange(0, 51, 5), np.arange(-20, 21, 4)], axis=1, weights=r.random((4, 800)))
+
+
+# ---------------------------------------------------------------- column layout (leading / middle axes reduced)
+@case
+def leading_axis_time_lat_lon():                  # reduce `time` of (time, lat, lon): kept axes trail
+    r = _rng(34)
+    x = r.standard_normal((40, 6, 8)).astype(np.float32)
+    return [x], dict(bins=np.linspace(-3, 3, 13), axis=0)
+
+
+@case
+def leading_axes_weighted_joint():
+    r = _rng(35)
+    x = r.standard_normal((7, 9, 33)); y = r.standard_normal((7, 9, 33))
+    return [x, y], dict(bins=[np.linspace(-3, 3, 7), np.linspace(-2, 2, 5)], axis=(1, 0), weights=r.random((7, 9, 33)))
+
+
+@case
+def middle_axis_nonuniform():
+    r = _rng(36)
+    x = r.standard_normal((3, 50, 40))
+    return [x], dict(bins=np.sort(r.uniform(-3, 3, 12)), axis=1, weights=r.standard_normal((3, 50, 40)).astype(np.float32))

@@ -12,9 +12,13 @@ from tests.golden.cases import CASES
 from xhistogram_b200 import core
 
 
-def _oracle_desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing):
+def _oracle_desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing,
+                      out_device=None, n_inner=0):
     def full(a, stride):
         a = np.asarray(a)
+        if n_inner > 1:   # column layout: (outer, N, inner) C-contiguous -> logical rows a*inner + m
+            assert a.flags.c_contiguous and a.size == M * N
+            return np.ascontiguousarray(a.reshape(M // n_inner, N, n_inner).transpose(0, 2, 1)).reshape(M, N)
         assert a.flags.c_contiguous and a.shape[1] == N
         if stride == 0:
             assert a.shape[0] == 1

@@ -269,3 +269,34 @@ def test_cabi_rejects_bad_requests():
                         _cabi.XH_HOST, 0, None, 0, None)
     h, _ = core.histogram(x, bins=np.array([1.0]))       # a single edge means zero bins, as in numpy
     assert h.shape == (0,)
+
+
+@pytest.mark.parametrize("shape,axis,nb", [((500, 40, 64), 0, 30), ((4, 300, 257), 1, 12), ((3000, 2000), 0, 100),
+                                           ((50, 20, 1000), (0, 1), 20), ((9, 70, 33), (1,), 400)])
+def test_column_layout_leading_axes(shape, axis, nb):
+    """Leading / middle axes reduced: the column-layout kernel (device-resident and through the host pipeline)."""
+    x = DeviceArray.normal(shape, np.float32, seed=51)
+    w = DeviceArray.uniform(shape, np.float32, seed=52)
+    xn, wn = x.to_numpy(), w.to_numpy()
+    e = np.linspace(-3, 3, nb + 1)
+    want = O.histogram(xn, bins=e, axis=axis)[0]
+    want_w = O.histogram(xn, bins=e, axis=axis, weights=wn)[0]
+    h, _ = core.histogram(x, bins=e, axis=axis)                       # device-resident
+    assert np.array_equal(h, want)
+    hw, _ = core.histogram(x, bins=e, axis=axis, weights=w)
+    assert_hist_equal(hw, want_w)
+    h, _ = core.histogram(xn, bins=e, axis=axis)                      # host arrays: staged slabs of the reduced axis
+    assert np.array_equal(h, want)
+    hw, _ = core.histogram(xn, bins=e, axis=axis, weights=wn)
+    assert_hist_equal(hw, want_w)
+    x.free(); w.free()
+
+
+def test_column_layout_large_host_pipeline_and_joint():
+    r = np.random.default_rng(53)
+    x = r.standard_normal((600, 200, 256)).astype(np.float32)         # 30.7M samples: several staged slabs
+    y = r.standard_normal((600, 200, 256)).astype(np.float32)
+    e = [np.linspace(-3, 3, 9), np.sort(r.uniform(-3, 3, 8))]
+    h, _ = core.histogram(x, y, bins=e, axis=0)
+    want = O.histogram(x, y, bins=e, axis=0, threads=8)[0]
+    assert np.array_equal(h, want)

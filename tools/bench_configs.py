@@ -112,6 +112,17 @@ def main():
     report("short rows weighted 1xfp32 (2e6,50) 20 bins axis=-1", M * N, M * N * 8 + M * 20 * 8, best, med, "row-tiled")
     x.free(); w.free()
 
+    # leading axis reduced (`dim="time"` on (time, lat, lon)): column-layout kernel, no transpose
+    T_, La, Lo = max(1, int(1000 * sc)), 512, 1024
+    x = DeviceArray.normal((T_, La, Lo), np.float32, seed=23); w = DeviceArray.uniform((T_, La, Lo), np.float32, seed=24)
+    e = np.linspace(-4, 4, 51)
+    _, best, med = timed([x], None, [e], [0], a.reps)
+    report("leading axis 1xfp32 (1000,512,1024) 50 bins axis=0", T_ * La * Lo, T_ * La * Lo * 4 + La * Lo * 50 * 8, best, med, "column layout")
+    e2 = np.linspace(-4, 4, 21)
+    _, best, med = timed([x], w, [e2], [0], a.reps)
+    report("leading axis weighted 1xfp32 (1000,512,1024) 20 bins axis=0", T_ * La * Lo, T_ * La * Lo * 8 + La * Lo * 20 * 8, best, med, "column layout")
+    x.free(); w.free()
+
     with open(os.path.join(ROOT, "gpurun_out", "bench_configs.json"), "w") as f:
         json.dump(rows, f, indent=1)
 

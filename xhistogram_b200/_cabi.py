@@ -54,6 +54,7 @@ class XhDesc(C.Structure):
         ("stream", C.c_void_p),
         ("kernel_ms", C.POINTER(C.c_float)),
         ("iedges", C.POINTER(C.c_int64) * XH_MAX_VARS),
+        ("n_inner", C.c_int64),
     ]
 
 

@@ -216,6 +216,26 @@ def set_default_device(device: int):
     _default_dev = int(device)
 
 
+_MIN_INNER_COLUMNS = 32
+
+
+def _column_layout(shape, axis):
+    """(outer, N, inner) when the reduced axes are one contiguous block followed by kept axes, else None.
+
+    Such a reduction (e.g. over ``time`` of a (time, lat, lon) array) needs a transposing copy in the reference
+    (np.moveaxis + reshape, core.py:218-226); the library's column-layout kernel reads it in place.
+    """
+    ax = sorted(axis)
+    if not ax or ax != list(_range(ax[0], ax[-1] + 1)) or ax[-1] == len(shape) - 1:
+        return None
+    outer = int(np.prod(shape[: ax[0]], dtype=np.int64))
+    n = int(np.prod(shape[ax[0]: ax[-1] + 1], dtype=np.int64))
+    inner = int(np.prod(shape[ax[-1] + 1:], dtype=np.int64))
+    if inner < _MIN_INNER_COLUMNS or n == 0:
+        return None
+    return outer, n, inner
+
+
 def _rows_view(a, axis, full):
     """(2-D C-contiguous host array or single row, row_stride, M, N) for the (kept, reduced) layout."""
     if full:
@@ -261,15 +281,21 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
                 raise ValueError("device inputs must all have the same shape (no broadcasting on the device path)")
         if len({v[2] for v in views}) != 1:
             raise TypeError("device inputs must share one dtype (float32 or float64)")
+        n_inner = 0
         if full:
             M, N = 1, int(np.prod(shape, dtype=np.int64))
-        else:
-            if sorted(axis) != list(_range(nd - len(axis), nd)):
-                raise NotImplementedError("device inputs support reducing the trailing axes only (or all axes)")
+        elif sorted(axis) == list(_range(nd - len(axis), nd)):
             N = int(np.prod(shape[nd - len(axis):], dtype=np.int64))
             M = int(np.prod(shape[: nd - len(axis)], dtype=np.int64))
+        else:
+            col = _column_layout(shape, axis)
+            if col is None:
+                raise NotImplementedError("device inputs support reducing one contiguous block of axes: the trailing axes, "
+                                          f"or leading/middle axes followed by at least {_MIN_INNER_COLUMNS} kept columns")
+            outer, N, n_inner = col
+            M = outer * n_inner
         dev = views[0][3]
-        out = _device_call(views, wview, bins, M, N, dev, _flags, _timing, _out_device)
+        out = _device_call(views, wview, bins, M, N, dev, _flags, _timing, _out_device, n_inner)
         if _out_device is not None:
             return out                                       # DeviceArray (M * prod(bins)), stays in HBM
         return out.reshape(kept_axes_shape + nbins)
@@ -285,12 +311,25 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
     if w is not None:
         w = _as_float_weights(np.asarray(w))
     ax = None if full else list(axis)
+    col = None if full else _column_layout(shape, ax)
+    if col is not None and (_devices is None or len(_devices) <= 1):
+        everything = data + ([w] if w is not None else [])
+        if all(a.shape == tuple(shape) and a.flags.c_contiguous for a in everything):
+            outer, N, n_inner = col
+            wdt = _xh_dtype(w.dtype) if w is not None else _cabi.XH_NONE
+            out = _desc_call(data, [N] * len(data), w, N if w is not None else 0, bins, outer * n_inner, N, xdt_of(iplan, data), wdt,
+                             _cabi.XH_HOST, _default_device(), None, _flags, _timing, None, n_inner)
+            return out.reshape(kept_axes_shape + nbins)
     rows = [_rows_view(a, ax, full) for a in data]
     M, N = rows[0][2], rows[0][3]
     wrow = _rows_view(w, ax, full) if w is not None else None
-    xdt = _cabi.XH_I64 if iplan is not None else _xh_dtype(data[0].dtype)
+    xdt = xdt_of(iplan, data)
     out = _host_call([r[0] for r in rows], [r[1] for r in rows], wrow, bins, M, N, xdt, _devices, _flags, _timing)
     return out.reshape(kept_axes_shape + nbins)
+
+
+def xdt_of(iplan, data):
+    return _cabi.XH_I64 if iplan is not None else _xh_dtype(data[0].dtype)
 
 
 def _host_call(arrs, strides, wrow, bins, M, N, xdt, devices, flags, timing):
@@ -300,21 +339,23 @@ def _host_call(arrs, strides, wrow, bins, M, N, xdt, devices, flags, timing):
                       devices[0] if devices else _default_device(), devices, flags, timing)
 
 
-def _device_call(views, wview, bins, M, N, dev, flags, timing, out_device=None):
+def _device_call(views, wview, bins, M, N, dev, flags, timing, out_device=None, n_inner=0):
     ptrs = [v[0] for v in views]
     wptr = wview[0] if wview else None
     wdt = _xh_dtype(wview[2]) if wview else _cabi.XH_NONE
     return _desc_call(ptrs, [N] * len(ptrs), wptr, N if wview else 0, bins, M, N, _xh_dtype(views[0][2]), wdt,
-                      _cabi.XH_DEVICE, dev, None, flags, timing, out_device)
+                      _cabi.XH_DEVICE, dev, None, flags, timing, out_device, n_inner)
 
 
-def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing, out_device=None):
+def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing, out_device=None,
+               n_inner=0):
     K = len(arrs)
     if K > _cabi.XH_MAX_VARS:
         raise NotImplementedError(f"at most {_cabi.XH_MAX_VARS} variables are supported")
     d = _cabi.XhDesc()
     d.n_vars, d.dtype, d.w_dtype, d.mem, d.out_mem, d.device, d.flags = K, dtype, wdtype, mem, _cabi.XH_HOST, device, flags | _debug_flags
     d.n_rows, d.n_cols = M, N
+    d.n_inner = n_inner
     keep = []
     for k in _range(K):
         if mem == _cabi.XH_HOST:

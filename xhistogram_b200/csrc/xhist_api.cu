@@ -443,6 +443,8 @@ int validate(const xh_desc* d) {
   }
   if (d->weights && reinterpret_cast<uintptr_t>(d->weights) % dsize(d->w_dtype)) return fail(XH_ERR_INVALID, "weights not element-aligned");
   if ((d->flags & XH_FLAG_NO_ZERO) && d->out_mem != XH_DEVICE) return fail(XH_ERR_INVALID, "XH_FLAG_NO_ZERO needs a device out");
+  if (d->n_inner > 1 && (d->n_rows % d->n_inner) != 0) return fail(XH_ERR_INVALID, "column layout: n_rows must be a multiple of n_inner");
+  if (d->n_inner < 0) return fail(XH_ERR_INVALID, "negative n_inner");
   return XH_OK;
 }
 
@@ -578,6 +580,82 @@ int run_host_pipeline(Ctx* c, const Prep& pr, const xh_desc* d, void* dev_out) {
   return XH_OK;
 }
 
+// ---- column layout (leading axes reduced): k_hist_cols ----------------------------------------------------
+// Threads per CTA = columns per CTA (tm): each thread keeps a private histogram of B bins in shared memory.
+int cols_tile(Ctx* c, const Prep& pr, const xh_desc* d, int* tm_out, size_t* smem_out) {
+  const long long B = pr.base.B;
+  const size_t item = d->w_dtype == XH_NONE ? 4 : 8;
+  const long long budget = static_cast<long long>(c->smem_optin) - 64 - static_cast<long long>(pr.edges_al);
+  long long tm = budget / static_cast<long long>(B * item);
+  tm = std::min<long long>(tm / 32 * 32, XHK_THREADS);
+  if (tm < 32) return fail(XH_ERR_UNSUPPORTED, "column layout: %lld bins per column do not fit a per-thread shared histogram", B);
+  // small problems: do not spread a few columns over a 1024-thread CTA
+  while (tm > 128 && d->n_inner <= tm / 2) tm /= 2;
+  *tm_out = static_cast<int>(tm);
+  *smem_out = pr.edges_al + static_cast<size_t>(B) * tm * item;
+  return XH_OK;
+}
+
+int run_cols_device(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, bool accumulate) {
+  int tm = 0; size_t smem = 0;
+  int rc = cols_tile(c, pr, d, &tm, &smem);
+  if (rc) return rc;
+  XhkParams p = pr.base;
+  p.M = d->n_rows; p.N = d->n_cols;
+  for (int k = 0; k < d->n_vars; ++k) p.data[k] = d->data[k];
+  p.w = d->weights; p.out = d->out; p.edges = c->edges; p.w_dtype = d->w_dtype;
+  p.lut = reinterpret_cast<const unsigned short*>(static_cast<const unsigned char*>(c->edges) + pr.lut_dev_off);
+  const long long inner = d->n_inner, outer = d->n_rows / inner;
+  const long long tiles = ((inner + tm - 1) / tm) * outer;
+  int nsplit = 1;
+  if (tiles < 2ll * c->sm_count) nsplit = static_cast<int>(std::min<long long>((2ll * c->sm_count + tiles - 1) / tiles, std::max<long long>(1, d->n_cols / 256)));
+  const bool acc = accumulate || nsplit > 1;
+  if (acc && !accumulate) CU(cudaMemsetAsync(d->out, 0, static_cast<size_t>(d->n_rows) * pr.base.B * 8, stream));
+  XhkLaunch l; l.dtype = d->dtype; l.w_dtype = d->w_dtype; l.grid = 0; l.threads = tm; l.smem_bytes = smem; l.stream = stream;
+  CU(xhk_launch_hist_cols(p, l, inner, tm, nsplit, acc ? 1 : 0));
+  return XH_OK;
+}
+
+// host inputs in column layout: stage slabs of the reduced axis (all inner columns of n0..n1) and accumulate
+int run_cols_host_pipeline(Ctx* c, const Prep& pr, const xh_desc* d, void* dev_out) {
+  const int K = d->n_vars;
+  const size_t tsz = dsize(d->dtype), wsz = dsize(d->w_dtype);
+  const long long inner = d->n_inner, outer = d->n_rows / inner, N = d->n_cols, B = pr.base.B;
+  const int narr = K + (wsz ? 1 : 0);
+  const long long chunk = 1ll << 23;
+  const long long rows_per = std::max<long long>(1, std::min<long long>(N, chunk / inner));
+  size_t slot_bytes = 0; std::vector<size_t> off(narr, 0);
+  for (int a = 0; a < narr; ++a) { off[a] = slot_bytes; slot_bytes += (static_cast<size_t>(rows_per) * inner * (a < K ? tsz : wsz) + 255) & ~static_cast<size_t>(255); }
+  int rc = ensure_stage(c, slot_bytes);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(dev_out, 0, static_cast<size_t>(d->n_rows) * B * 8, c->stream));
+  int it = 0;
+  for (long long a = 0; a < outer; ++a) {
+    for (long long n0 = 0; n0 < N; n0 += rows_per) {
+      const long long nc = std::min(rows_per, N - n0);
+      const int slot = it & 1; ++it;
+      unsigned char* base = static_cast<unsigned char*>(c->stage[slot]);
+      CU(cudaStreamWaitEvent(c->copy_stream, c->consumed[slot], 0));
+      xh_desc b = *d;
+      b.mem = XH_DEVICE; b.out_mem = XH_DEVICE; b.kernel_ms = nullptr;
+      b.n_rows = inner; b.n_cols = nc; b.n_inner = inner;
+      b.out = static_cast<unsigned char*>(dev_out) + static_cast<size_t>(a) * inner * B * 8;
+      for (int q = 0; q < narr; ++q) {
+        const size_t es = q < K ? tsz : wsz;
+        const unsigned char* src = static_cast<const unsigned char*>(q < K ? d->data[q] : d->weights) + (static_cast<size_t>(a) * N + n0) * inner * es;
+        CU(cudaMemcpyAsync(base + off[q], src, static_cast<size_t>(nc) * inner * es, cudaMemcpyHostToDevice, c->copy_stream));
+        if (q < K) b.data[q] = base + off[q]; else b.weights = base + off[q];
+      }
+      CU(cudaEventRecord(c->copied[slot], c->copy_stream));
+      CU(cudaStreamWaitEvent(c->stream, c->copied[slot], 0));
+      rc = run_cols_device(c, pr, &b, c->stream, true);
+      if (rc) return rc;
+      CU(cudaEventRecord(c->consumed[slot], c->stream));
+    }
+  }
+  return XH_OK;
+}
+
 int hist_locked(Ctx* c, const xh_desc* d) {
   CU(cudaSetDevice(c->device));
   const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
@@ -602,7 +680,14 @@ int hist_locked(Ctx* c, const xh_desc* d) {
   } else {
     rc = upload_edges(c, pr, s);
     if (rc == XH_OK) {
-      if (d->mem == XH_DEVICE) {
+      if (d->n_inner > 1) {
+        if (d->mem == XH_DEVICE) {
+          xh_desc b = *d; b.out = dev_out; b.out_mem = XH_DEVICE;
+          rc = run_cols_device(c, pr, &b, s, (d->flags & XH_FLAG_NO_ZERO) != 0);
+        } else {
+          rc = run_cols_host_pipeline(c, pr, d, dev_out);
+        }
+      } else if (d->mem == XH_DEVICE) {
         xh_desc b = *d; b.out = dev_out; b.out_mem = XH_DEVICE;
         rc = run_device_block(c, pr, &b, s);
       } else {
@@ -694,6 +779,7 @@ int xh_hist_multi(const xh_desc* d, const int32_t* devices, int32_t n_dev) {
   if (!devices || n_dev < 1) return fail(XH_ERR_INVALID, "need at least one device");
   if (d->mem != XH_HOST || d->out_mem != XH_HOST) return fail(XH_ERR_INVALID, "xh_hist_multi takes host data and a host out");
   if (n_dev == 1) { xh_desc b = *d; b.device = devices[0]; return xh_hist(&b); }
+  if (d->n_inner > 1) return fail(XH_ERR_UNSUPPORTED, "xh_hist_multi does not take the column layout; shard the kept axis on the caller side");
   const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
   const size_t tsz = dsize(d->dtype), wsz = dsize(d->w_dtype);
   std::vector<Ctx*> ctx(n_dev);

@@ -727,6 +727,111 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// column layout: reductions over LEADING axes.  The arrays are (n_outer, N, inner) C-contiguous blocks and the
+// histogram is taken over N for every (a, m).  One thread owns one kept column m: it walks down the reduced axis
+// (adjacent threads read adjacent addresses: coalesced) and accumulates into a thread-PRIVATE histogram
+// hist[bin][thread] in shared memory — plain read-modify-write, no atomics, conflict-free banks; weighted sums are
+// added in sample order like np.bincount.  The reference has to copy for this layout (np.moveaxis + reshape,
+// core.py:218-226).  grid = (n_outer * column tiles, nsplit slices of the reduced axis).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int W, int KT>
+__global__ void __launch_bounds__(kMaxThreads, 1) k_hist_cols(const __grid_constant__ XhkParams p, long long inner, int tm, int accumulate) {
+  using HT = typename std::conditional<W == 0, unsigned int, double>::type;
+  using OT = typename std::conditional<W == 0, unsigned long long, double>::type;
+  using WT = typename WType<W>::type;
+  constexpr int KMAX = KT ? KT : XHK_MAX_VARS;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int K = KT ? KT : p.n_vars;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  T* sedges = reinterpret_cast<T*>(smem);
+  const size_t edges_al = (static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15);
+  unsigned short* slut = reinterpret_cast<unsigned short*>(smem + edges_al);
+  HT* hist = reinterpret_cast<HT*>(smem + edges_al + ((static_cast<size_t>(p.n_lut_total) * 2 + 15) & ~static_cast<size_t>(15)));
+  for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
+  for (int i = tid; i < p.n_lut_total; i += nthr) slut[i] = p.lut[i];
+  const int B = static_cast<int>(p.B);
+  for (int i = tid; i < B * tm; i += nthr) hist[i] = HT(0);
+  __syncthreads();
+
+  const long long tiles = (inner + tm - 1) / tm;
+  const long long a = blockIdx.x / tiles;
+  const long long m0 = (blockIdx.x - a * tiles) * tm;
+  const long long m = m0 + tid;
+  const long long N = p.N;
+  const long long n0 = N * blockIdx.y / gridDim.y, n1 = N * (blockIdx.y + 1ll) / gridDim.y;
+  if (tid < tm && m < inner) {
+    const T* px[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) px[k] = (k < K) ? static_cast<const T*>(p.data[k]) + a * N * inner + m : nullptr;
+    const WT* pw = (W != 0) ? static_cast<const WT*>(p.w) + a * N * inner + m : nullptr;
+    auto one = [&](const T (&x)[KMAX], WT wv) {
+      int bin = 0; bool ok = true;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          const int j = exact_bin_inline<T>(p, k, sedges, slut, x[k]);
+          ok = ok && j >= 0;
+          bin = bin * p.nb[k] + j;
+        }
+      }
+      if (ok) {
+        HT* h = hist + static_cast<size_t>(bin) * tm + tid;
+        if constexpr (W == 0) *h += 1u; else *h += static_cast<double>(wv);
+      }
+    };
+    // rows of the reduced axis in flight per thread (4-byte loads: keep ~32 B per thread outstanding)
+    constexpr int UN = (sizeof(T) * KMAX + (W == 0 ? 0 : sizeof(WT)) <= 8) ? 8 : 4;
+    long long n = n0;
+    for (; n + UN <= n1; n += UN) {
+      T xv[UN][KMAX]; WT wv[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) if (k < K) xv[u][k] = __ldcs(px[k] + (n + u) * inner);
+        wv[u] = WT(1);
+        if constexpr (W != 0) wv[u] = __ldcs(pw + (n + u) * inner);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) one(xv[u], wv[u]);
+    }
+    for (; n < n1; ++n) {
+      T x[KMAX]; WT wv = WT(1);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) if (k < K) x[k] = px[k][n * inner];
+      if constexpr (W != 0) wv = pw[n * inner];
+      one(x, wv);
+    }
+  }
+  __syncthreads();
+  // flush: consecutive threads write consecutive bins of one output row (coalesced); out row = a*inner + m
+  OT* out = static_cast<OT*>(p.out) + (a * inner + m0) * B;
+  const long long cols = (inner - m0 < tm) ? inner - m0 : tm;
+  for (long long i = tid; i < cols * B; i += nthr) {
+    const int ml = static_cast<int>(i / B), b = static_cast<int>(i - static_cast<long long>(ml) * B);
+    const HT v = hist[static_cast<size_t>(b) * tm + ml];
+    if (accumulate) { if (v != HT(0)) atomicAdd(out + i, static_cast<OT>(v)); }
+    else out[i] = static_cast<OT>(v);
+  }
+}
+
+typedef void (*ColsKernel)(const XhkParams, long long, int, int);
+template <typename T, int W>
+ColsKernel pick_cols_k(int K) {
+  switch (K) {
+    case 1: return k_hist_cols<T, W, 1>;
+    case 2: return k_hist_cols<T, W, 2>;
+    case 3: return k_hist_cols<T, W, 3>;
+    case 4: return k_hist_cols<T, W, 4>;
+    default: return k_hist_cols<T, W, 0>;
+  }
+}
+template <typename T>
+ColsKernel pick_cols_w(int w, int K) { return w == 0 ? pick_cols_k<T, 0>(K) : w == 1 ? pick_cols_k<T, 1>(K) : pick_cols_k<T, 2>(K); }
+ColsKernel pick_cols(int dtype, int w, int K) {
+  return dtype == 1 ? pick_cols_w<float>(w, K) : dtype == 2 ? pick_cols_w<double>(w, K) : pick_cols_w<long long>(w, K);
+}
+
 // zero the rows of `out` that are shared between CTAs under the sample partition (XHK_FULL only)
 template <typename OT>
 __global__ void k_zero_shared_rows(const __grid_constant__ XhkParams p, int hist_grid) {
@@ -875,6 +980,12 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
         }
   // k_window has a little more static shared memory than k_hist
   for (int dt = 1; dt <= 3; ++dt)
+    for (int w = 0; w <= 2; ++w)
+      for (int k = 0; k <= 4; ++k) {
+        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_cols(dt, w, k)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+        if (e != cudaSuccess) return e;
+      }
+  for (int dt = 1; dt <= 3; ++dt)
     for (int k = 0; k <= 4; ++k) {
       cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_window(dt, k)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 192);
       if (e != cudaSuccess) return e;
@@ -885,6 +996,13 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
 cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l) {
   HistKernel k = pick(l.dtype, l.w_dtype, p.n_vars, kernel_mode(p, l.dtype));
   k<<<l.grid, l.threads, l.smem_bytes, l.stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t xhk_launch_hist_cols(const XhkParams& p, const XhkLaunch& l, long long inner, int tm, int nsplit, int accumulate) {
+  const long long outer = p.M / inner;
+  dim3 grid(static_cast<unsigned>(((inner + tm - 1) / tm) * outer), static_cast<unsigned>(nsplit), 1);
+  pick_cols(l.dtype, l.w_dtype, p.n_vars)<<<grid, l.threads, l.smem_bytes, l.stream>>>(p, inner, tm, accumulate);
   return cudaGetLastError();
 }
 

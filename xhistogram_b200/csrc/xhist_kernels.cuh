@@ -99,6 +99,9 @@ struct XhkLaunch {
 
 // host-callable launchers (defined in xhist_kernels.cu)
 cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l);
+// column layout: p.M = n_outer * n_inner logical rows, p.N reduced length, inner = n_inner; tm columns per CTA,
+// nsplit CTAs share the reduced axis of one column tile (nsplit > 1 -> atomic flush into a zeroed out)
+cudaError_t xhk_launch_hist_cols(const XhkParams& p, const XhkLaunch& l, long long inner, int tm, int nsplit, int accumulate);
 cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow* window_dev, int budget_bins, int n_probe);
 cudaError_t xhk_launch_zero_shared_rows(const XhkParams& p, const XhkLaunch& l);
 cudaError_t xhk_set_smem_limits(int max_optin);

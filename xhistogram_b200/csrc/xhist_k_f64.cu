@@ -1,0 +1,3 @@
+// double instantiations of the histogram kernels (see xhist_kernels_impl.cuh / xhist_kernels.cu)
+#include "xhist_kernels_impl.cuh"
+XHK_DEFINE_PICKERS(f64, double, true)

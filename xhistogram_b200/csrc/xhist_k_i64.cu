@@ -1,0 +1,3 @@
+// long long instantiations of the histogram kernels (see xhist_kernels_impl.cuh / xhist_kernels.cu)
+#include "xhist_kernels_impl.cuh"
+XHK_DEFINE_PICKERS(i64, long long, false)

@@ -12,825 +12,12 @@
 // Design numbers (profiles/r1_microbench_mechanisms.log, B200): streaming 12 B/sample reaches
 // ~7.0 TB/s; shared u32 atomics are free next to the stream (~590 Gsamples/s); shared f64 CAS adds
 // reach ~340 Gsamples/s; global RED only 88 Gsamples/s — hence everything that can be privatised is.
+// Source layout: the kernel templates live in xhist_kernels_impl.cuh and are instantiated per data type in
+// xhist_k_f32.cu / xhist_k_f64.cu / xhist_k_i64.cu (parallel compilation); this file holds the small utility
+// kernels and the host-callable launchers.
 #include "xhist_kernels.cuh"
-#include <type_traits>
 
 namespace {
-
-constexpr int kMaxThreads = XHK_THREADS;
-constexpr long long kSegCap = 1ll << 30;  // u32 shared counters are flushed at least this often
-
-template <typename T> struct Consts;
-template <> struct Consts<float> {
-  static __device__ __forceinline__ float get(const XhkParams& p, int k, int i) { return p.cf[k][i]; }
-};
-template <> struct Consts<double> {
-  static __device__ __forceinline__ double get(const XhkParams& p, int k, int i) { return p.cd[k][i]; }
-};
-template <> struct Consts<long long> {   // int64 data (integers, datetime64 ticks): range limits only
-  static __device__ __forceinline__ long long get(const XhkParams& p, int k, int i) { return i < 2 ? p.ci[k][i] : 0ll; }
-};
-
-__device__ __forceinline__ int floor_to_int(float t) { return __float2int_rd(t); }
-__device__ __forceinline__ int floor_to_int(double t) { return __double2int_rd(t); }
-__device__ __forceinline__ int floor_to_int(long long t) { return static_cast<int>(t); }   // never used (no uniform / table path for int64)
-
-// shared-memory atomics on explicit 32-bit shared addresses (no generic->shared conversion per use)
-__device__ __forceinline__ void reds_add_u32(unsigned addr, unsigned v) {
-  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned atoms_add_u32(unsigned addr, unsigned v) {
-  unsigned old;
-  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
-  return old;
-}
-__device__ __forceinline__ void reds_add_f64(unsigned addr, double v) {
-  asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
-}
-__device__ __forceinline__ long long to_ll_rn(float v) { return __float2ll_rn(v); }
-__device__ __forceinline__ long long to_ll_rn(double v) { return __double2ll_rn(v); }
-
-// ---------------------------------------------------------------------------------------------
-// classification: bin of x for variable k, or -1 when x is dropped.
-// Rule R1 of SURVEY.md §8a == core.py:157-174: in range iff e[0] <= x <= e[E-1]; bin =
-// #{j: e[j] <= x} - 1 with x == e[E-1] falling in the last bin.  `e` holds the EFFECTIVE edges:
-// for fp32 data each float64 edge is replaced by the smallest fp32 >= edge, which makes an fp32
-// compare decide exactly like numpy's promoted float64 compare (rule R2).
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ int search_bin(const T* __restrict__ e, int nb, T x) {
-  int lo = 0, hi = nb + 1;  // #{e[j] <= x} is in [lo, hi]
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (e[mid] <= x) lo = mid + 1; else hi = mid;
-  }
-  int b = lo - 1;
-  return b > nb - 1 ? nb - 1 : b;  // right-inclusive last bin (core.py:171-173)
-}
-
-// Uniform-edge arithmetic.  t = (x - e0) * inv is within delta/2 of the exact position of x in
-// bin units (bound computed on the host from the rounding errors and from the deviation of the
-// edges from an arithmetic progression), so j = floor(t) is THE bin whenever
-// delta <= frac(t) <= 1 - delta and 0 <= j < nb; only the other samples (~1e-4) need the search.
-template <typename T>
-__device__ __forceinline__ bool uniform_guess(const XhkParams& p, int k, T x, int& j) {
-  const T t = (x - Consts<T>::get(p, k, XHK_C_E0)) * Consts<T>::get(p, k, XHK_C_INV);
-  j = floor_to_int(t);                // NaN -> 0, +-inf / huge -> saturated: both fail the tests below
-  const T f = t - static_cast<T>(j);  // NaN stays NaN: compares false
-  return (f >= Consts<T>::get(p, k, XHK_C_DELTA)) & (f <= Consts<T>::get(p, k, XHK_C_OMD));
-}
-
-// exact bin of any sample (slow but general): range test, uniform guess when usable, else search
-template <typename T> __device__ __forceinline__ T lut_inv(const XhkParams& p, int k);
-template <> __device__ __forceinline__ float lut_inv<float>(const XhkParams& p, int k) { return p.lut_invf[k]; }
-template <> __device__ __forceinline__ double lut_inv<double>(const XhkParams& p, int k) { return p.lut_invd[k]; }
-template <> __device__ __forceinline__ long long lut_inv<long long>(const XhkParams&, int) { return 0ll; }
-
-// Non-uniform edges: the cell of x in a uniform partition of [lo, hi] brackets #{e_j <= x} between the table
-// entries of cell c-1 and cell c+2 (one cell of slack on either side absorbs the rounding of the cell index),
-// so the binary search runs over a handful of edges instead of all of them.
-template <typename T>
-__device__ __forceinline__ int lut_bin(const XhkParams& p, int k, const T* __restrict__ e, const unsigned short* __restrict__ lut, T x) {
-  const int nb = p.nb[k], G = p.lut_n[k];
-  int c = floor_to_int((x - Consts<T>::get(p, k, XHK_C_LO)) * lut_inv<T>(p, k));
-  c = max(0, min(c, G - 1));
-  int lo = static_cast<int>(lut[max(c - 1, 0)]) + 1;                       // e[lo-1] <= x is known
-  int hi = (c + 2 < G) ? static_cast<int>(lut[c + 2]) + 1 : nb + 1;         // #{e_j <= x} <= hi
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (e[mid - 1] <= x) lo = mid; else hi = mid - 1;
-  }
-  const int b = lo - 1;
-  return b > nb - 1 ? nb - 1 : b;
-}
-
-template <typename T>
-__device__ __forceinline__ int exact_bin_inline(const XhkParams& p, int k, const T* __restrict__ sedges,
-                                                const unsigned short* __restrict__ slut, T x) {
-  if (!(x >= Consts<T>::get(p, k, XHK_C_LO) && x <= Consts<T>::get(p, k, XHK_C_HI))) return -1;  // NaN: dropped (rule R3)
-  const int nb = p.nb[k];
-  if (p.uniform[k]) {
-    int j;
-    if (uniform_guess<T>(p, k, x, j) && static_cast<unsigned>(j) < static_cast<unsigned>(nb)) return j;
-  }
-  if (p.lut_n[k]) return lut_bin<T>(p, k, sedges + p.eoff[k], slut + p.lut_off[k], x);
-  return search_bin<T>(sedges + p.eoff[k], nb, x);
-}
-// out-of-line copy for the rare exact path of the fast kernel (keeps its hot loop small)
-template <typename T>
-__device__ __noinline__ int exact_bin(const XhkParams& p, int k, const T* __restrict__ sedges,
-                                      const unsigned short* __restrict__ slut, T x) {
-  return exact_bin_inline<T>(p, k, sedges, slut, x);
-}
-
-// ---------------------------------------------------------------------------------------------
-// streaming loads (one-touch data: evict-first)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load4(const float* p, long long g, float (&v)[4]) {
-  float4 q = __ldcs(reinterpret_cast<const float4*>(p) + g);
-  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-}
-__device__ __forceinline__ void load4(const long long* p, long long g, long long (&v)[4]) {
-  longlong2 a = __ldcs(reinterpret_cast<const longlong2*>(p) + 2 * g);
-  longlong2 b = __ldcs(reinterpret_cast<const longlong2*>(p) + 2 * g + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-__device__ __forceinline__ void load4(const double* p, long long g, double (&v)[4]) {
-  double2 a = __ldcs(reinterpret_cast<const double2*>(p) + 2 * g);
-  double2 b = __ldcs(reinterpret_cast<const double2*>(p) + 2 * g + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-
-template <int W> struct WType { using type = float; };
-template <> struct WType<2> { using type = double; };
-
-// ---------------------------------------------------------------------------------------------
-// the histogram kernel
-//   T    : data type (float / double)        W : 0 no weights, 1 fp32 weights, 2 fp64 weights
-//   KT   : number of variables at compile time (1..4), or 0 = runtime p.n_vars (scalar loads only)
-//   MODE : 0 general (per-sample exact classification: range test, uniform guess / table-bracketed search)
-//          1 every variable has evenly spaced edges -> branch-free arithmetic classification of 8 samples at a
-//            time; samples that are uncertain or fall outside the shared window take a side path
-//          2 every variable is uniform or has a bounded-step lookup table -> branch-free classification of
-//            4 samples at a time, window spills as inline global REDs
-// ---------------------------------------------------------------------------------------------
-template <typename T, int W, int KT, int MODE>
-__global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__ XhkParams p) {
-  constexpr bool FAST = (MODE == 1);
-  using HT = typename std::conditional<W == 0, unsigned int, double>::type;          // shared accumulator
-  using OT = typename std::conditional<W == 0, unsigned long long, double>::type;    // global accumulator
-  using WT = typename WType<W>::type;
-  constexpr int KMAX = KT ? KT : XHK_MAX_VARS;
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ int s_wlo[XHK_MAX_VARS], s_wlen[XHK_MAX_VARS];
-
-  const int K = KT ? KT : p.n_vars;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  T* sedges = reinterpret_cast<T*>(smem);
-  const size_t edges_al = (static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15);
-  unsigned short* slut = reinterpret_cast<unsigned short*>(smem + edges_al);
-  HT* shist = reinterpret_cast<HT*>(smem + edges_al + ((static_cast<size_t>(p.n_lut_total) * 2 + 15) & ~static_cast<size_t>(15)));
-
-  for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
-  for (int i = tid; i < p.n_lut_total; i += nthr) slut[i] = p.lut[i];
-  if (tid < XHK_MAX_VARS) {
-    int lo = 0, len = 0;
-    if (tid < K) {
-      if (p.hist_mode == XHK_WINDOW) { lo = p.window->lo[tid]; len = p.window->len[tid]; }
-      else if (p.hist_mode == XHK_FULL) { lo = 0; len = p.nb[tid]; }
-    }
-    s_wlo[tid] = lo; s_wlen[tid] = len;
-  }
-  __syncthreads();
-  int wlo[KMAX], wlen[KMAX];
-  int wtot = (p.hist_mode == XHK_GLOBAL) ? 0 : 1;
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    if (k < K) { wlo[k] = s_wlo[k]; wlen[k] = s_wlen[k]; wtot *= wlen[k]; } else { wlo[k] = 0; wlen[k] = 0; }
-  }
-  // row tiling: the shared histogram holds tile_rows rows; a sample's bin is offset by (local row) * (bins per row),
-  // obtained for free by seeding the Horner evaluation of the joint bin with the local row
-  const bool tiled = p.tile_rows > 1;
-  wtot *= p.tile_rows;
-  for (int i = tid; i < (W == 0 ? wtot : wtot + 32); i += nthr) shist[i] = HT(0);
-  // weighted accumulation mode (uniform for the launch): exact fixed point in two u32 limbs, or float64 adds
-  bool fx = false; WT fx_mul = WT(0), fx_limit = WT(0); double fx_unmul = 0.0;
-  if constexpr (W != 0) {
-    if (p.hist_mode != XHK_GLOBAL && p.window->fx_ok) {
-      fx = true; fx_mul = static_cast<WT>(p.window->fx_mul); fx_limit = static_cast<WT>(p.window->fx_limit); fx_unmul = p.window->fx_unmul;
-    }
-  }
-  // fixed-point layout: [wtot low limbs][32 trash slots][wtot high limbs][32 trash slots]; a lane with nothing
-  // to add puts a zero into its own trash slot, which keeps the weighted shared adds free of branches
-  const int wcap = wtot + 32;
-  const unsigned sh_lo = static_cast<unsigned>(__cvta_generic_to_shared(shist));   // counts / lo limbs / doubles
-  const unsigned sh_hi = sh_lo + 4u * static_cast<unsigned>(wcap);                  // hi limbs (fixed point)
-  const unsigned trash = static_cast<unsigned>(wtot + (tid & 31));
-  __syncthreads();
-
-  OT* const out = static_cast<OT*>(p.out);
-  const long long total = p.M * p.N;
-  long long s0, s1;
-  if (p.partition == XHK_PART_ROWS) {
-    s0 = (p.M * blockIdx.x / gridDim.x) * p.N;
-    s1 = (p.M * (blockIdx.x + 1ll) / gridDim.x) * p.N;
-  } else {
-    s0 = blockIdx.x * p.per_cta; if (s0 > total) s0 = total;
-    s1 = s0 + p.per_cta; if (s1 > total) s1 = total;
-  }
-
-  // ---- accumulation primitives ------------------------------------------------------------
-  auto global_add = [&](OT* out_row, long long gbin, double wv) {
-    if constexpr (W == 0) atomicAdd(out_row + gbin, 1ull); else atomicAdd(out_row + gbin, wv);
-  };
-  // general path of one sample: exact bins, then shared window / global spill / drop.
-  // Returns the window bin when the caller should do the shared add itself, else -1.
-  auto general_sample = [&](const T (&x)[KMAX], double wv, OT* out_row, int rowl) -> int {
-    int j[KMAX]; int wbin = rowl; bool ok = true, inwin = true;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < K) {
-        j[k] = FAST ? exact_bin<T>(p, k, sedges, slut, x[k]) : exact_bin_inline<T>(p, k, sedges, slut, x[k]);
-        ok = ok && (j[k] >= 0);
-        const unsigned jw = static_cast<unsigned>(j[k] - wlo[k]);
-        inwin = inwin && (jw < static_cast<unsigned>(wlen[k]));   // also false for j == -1
-        wbin = wbin * wlen[k] + static_cast<int>(jw);
-      }
-    }
-    if (inwin) return wbin;
-    if (ok) {
-      long long gbin = 0;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) if (k < K) gbin = gbin * p.nb[k] + j[k];
-      global_add(out_row, gbin, wv);
-    }
-    return -1;
-  };
-  // window bin -> global bin (rare paths only)
-  auto window_to_global = [&](int wbin) -> long long {
-    if (p.hist_mode == XHK_FULL) return wbin;     // the window is the whole (possibly tiled) bin space
-    int rem = wbin; long long gbin = 0;
-#pragma unroll
-    for (int k = KMAX - 1; k >= 0; --k) {
-      if (k < K) { const int q = rem / wlen[k]; const int c = rem - q * wlen[k]; rem = q; gbin += (wlo[k] + c) * p.gmul[k]; }
-    }
-    return gbin;
-  };
-  // shared add of one sample.
-  //  counts   : native RED.ADD.U32.
-  //  weighted : fixed point (fx) — v = w * 2^-s as a 64-bit integer split over two u32 limbs: one native
-  //             ATOMS.ADD on the low limb (its return value gives the carry) and a RED on the high limb when
-  //             it is non-zero.  Integer adds are exact and order independent; a weight that is not an exact
-  //             multiple of 2^s below the limit (also NaN/inf) goes to a float64 global RED instead.
-  //             Otherwise float64 adds in shared memory (red.shared.add.f64 = LDS + DADD + ATOMS.CAST.SPIN loop;
-  //             an explicit atomicCAS loop compiles to plain ATOMS.CAS.64 and measured >4x slower on B200).
-  auto shared_add1 = [&](int wbin, WT w, OT* out_row) {
-    if constexpr (W == 0) {
-      reds_add_u32(sh_lo + 4u * static_cast<unsigned>(wbin), 1u);
-    } else {
-      if (fx) {
-        const WT vs = w * fx_mul;
-        const long long v = to_ll_rn(vs);
-        if ((static_cast<WT>(v) == vs) & (fabs(vs) < fx_limit)) {
-          const unsigned lo = static_cast<unsigned>(v);
-          unsigned hi = static_cast<unsigned>(static_cast<unsigned long long>(v) >> 32);
-          const unsigned old = atoms_add_u32(sh_lo + 4u * static_cast<unsigned>(wbin), lo);
-          hi += (old + lo < old) ? 1u : 0u;
-          if (hi) reds_add_u32(sh_hi + 4u * static_cast<unsigned>(wbin), hi);
-        } else {
-          atomicAdd(out_row + window_to_global(wbin), static_cast<double>(w));
-        }
-      } else {
-        reds_add_f64(sh_lo + 8u * static_cast<unsigned>(wbin), static_cast<double>(w));
-      }
-    }
-  };
-  auto shared_add4 = [&](const int (&wb)[4], const WT (&wv)[4], OT* out_row) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) if (wb[e] >= 0) shared_add1(wb[e], wv[e], out_row);
-  };
-
-  long long s = s0;
-  while (s < s1) {
-    const long long r = s / p.N;
-    const long long c0 = s - r * p.N;
-    long long len = p.N - c0;
-    if (len > s1 - s) len = s1 - s;
-    if (len > kSegCap) len = kSegCap;
-    OT* out_row = out + r * p.B;
-
-    const T* px[KMAX];
-    bool vec_ok = (KT != 0);
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-      px[k] = (k < K) ? static_cast<const T*>(p.data[k]) + r * p.stride[k] + c0 : nullptr;
-    const WT* pw = (W != 0) ? static_cast<const WT*>(p.w) + r * p.wstride + c0 : nullptr;
-    long long head = ((16 - (reinterpret_cast<uintptr_t>(px[0]) & 15)) & 15) / sizeof(T);
-    if (head > len) head = len;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-      if (k < K) vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(px[k] + head) & 15) == 0);
-    if (W != 0) vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(pw + head) & 15) == 0);
-    if (!vec_ok) head = len;
-    const long long nvec = (len - head) >> 2;  // groups of 4 samples
-    const long long tail0 = head + (nvec << 2);
-
-    // local row of sample i of this segment inside its tile (0 without tiling)
-    auto local_row = [&](long long i) -> int {
-      if (!tiled) return 0;
-      const unsigned n = static_cast<unsigned>(c0 + i);
-      return static_cast<int>((__umulhi(n, p.tile_magic) + n) >> p.tile_shift);
-    };
-    // scalar head and tail (and everything when the arrays are not mutually 16-byte alignable)
-    auto scalar_at = [&](long long i) {
-      T x[KMAX];
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) x[k] = (k < K) ? px[k][i] : T(0);
-      WT wv[4] = {WT(1), WT(1), WT(1), WT(1)};
-      if constexpr (W != 0) wv[0] = pw[i];
-      const int wbin = general_sample(x, static_cast<double>(wv[0]), out_row, local_row(i));
-      if (wbin >= 0) shared_add1(wbin, wv[0], out_row);
-    };
-    for (long long i = tid; i < head; i += nthr) scalar_at(i);
-    for (long long i = tail0 + tid; i < len; i += nthr) scalar_at(i);
-
-    if constexpr (KT != 0) {
-      // vector body: 4 samples per 16-byte load, U loads in flight per array and thread
-      constexpr int U = (sizeof(T) * KMAX + (W == 0 ? 0 : sizeof(WT)) <= 12) ? 2 : 1;
-      for (long long g = tid; g < nvec; g += static_cast<long long>(U) * nthr) {
-        T xv[U][KMAX][4];
-        WT wv[U][4];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const long long gu = g + static_cast<long long>(u) * nthr;
-          if (gu < nvec) {
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) load4(px[k] + head, gu, xv[u][k]);
-            if constexpr (W != 0) load4(pw + head, gu, wv[u]);
-          }
-          if constexpr (W == 0) { wv[u][0] = wv[u][1] = wv[u][2] = wv[u][3] = WT(1); }
-        }
-        int wb[U][4];
-        if constexpr (MODE == 2) {
-          // ---- branch-free classification for mixed uniform / non-uniform variables.
-          // Non-uniform: the table entry of cell c-1 is a bin at or below the sample's; at most lut_steps edges
-          // lie between that cell's left boundary and the sample, so that many compare-and-advance steps give
-          // the exact bin.  The steps run over the 4 samples of a group together (independent LDS chains).
-          unsigned unsure = 0;
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const bool live = g + static_cast<long long>(u) * nthr < nvec;
-            int jb[KMAX][4]; bool okr[4], cert[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { okr[e] = live; cert[e] = live; }
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-              if (p.uniform[k]) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  cert[e] = cert[e] & uniform_guess<T>(p, k, xv[u][k][e], jb[k][e]);
-                  okr[e] = okr[e] & (static_cast<unsigned>(jb[k][e]) < static_cast<unsigned>(p.nb[k]));
-                }
-              } else {
-                const T lo = Consts<T>::get(p, k, XHK_C_LO), hi = Consts<T>::get(p, k, XHK_C_HI), inv = lut_inv<T>(p, k);
-                const int G = p.lut_n[k], nb = p.nb[k], steps = p.lut_steps[k];
-                const unsigned short* lut = slut + p.lut_off[k];
-                const T* ed = sedges + p.eoff[k];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const T x = xv[u][k][e];
-                  okr[e] = okr[e] & (x >= lo) & (x <= hi);          // NaN: false
-                  int c = floor_to_int((x - lo) * inv);
-                  c = max(0, min(c, G - 1));
-                  jb[k][e] = static_cast<int>(lut[max(c - 1, 0)]);
-                }
-                for (int st = 0; st < steps; ++st) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const int nx = min(jb[k][e] + 1, nb);
-                    jb[k][e] = (ed[nx] <= xv[u][k][e]) ? nx : jb[k][e];
-                  }
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) jb[k][e] = min(jb[k][e], nb - 1);   // right-inclusive last bin
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              bool inwin = true; int wbin = local_row(head + 4 * (g + static_cast<long long>(u) * nthr) + e), gbin = 0;
-#pragma unroll
-              for (int k = 0; k < KMAX; ++k) {
-                const unsigned jw = static_cast<unsigned>(jb[k][e] - wlo[k]);
-                inwin = inwin & (jw < static_cast<unsigned>(wlen[k]));
-                wbin = wbin * wlen[k] + static_cast<int>(jw);
-                gbin = gbin * p.nb[k] + jb[k][e];
-              }
-              const bool good = cert[e] & okr[e];
-              wb[u][e] = (good & inwin) ? wbin : -1;
-              if (good & !inwin) {                      // in range, outside the shared window: one global RED
-                if constexpr (W == 0) atomicAdd(out_row + gbin, 1ull);
-                else atomicAdd(out_row + gbin, static_cast<double>(wv[u][e]));
-              }
-              unsure |= (live & !cert[e]) ? (1u << (4 * u + e)) : 0u;
-            }
-          }
-          while (unsure) {   // rare: uncertain samples of uniform variables -> exact path
-            const int idx = __ffs(unsure) - 1;
-            unsure &= unsure - 1;
-            T x[KMAX]; WT wsel = WT(1);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (idx == 4 * u + e) {
-#pragma unroll
-                  for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
-                  wsel = wv[u][e];
-                }
-            const int wbin = general_sample(x, static_cast<double>(wsel), out_row,
-                                            local_row(head + 4 * (g + static_cast<long long>(idx >> 2) * nthr) + (idx & 3)));
-            if (wbin >= 0) shared_add1(wbin, wsel, out_row);
-          }
-        } else if constexpr (FAST) {
-          // phase A (branch-free, U*4*K independent chains): guess, certainty, window test
-          unsigned side = 0;   // bit (4u+e) set: that sample needs the side path
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const bool live = g + static_cast<long long>(u) * nthr < nvec;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              bool good = true; int wbin = local_row(head + 4 * (g + static_cast<long long>(u) * nthr) + e);
-#pragma unroll
-              for (int k = 0; k < KMAX; ++k) {
-                int j;
-                const bool certain = uniform_guess<T>(p, k, xv[u][k][e], j);
-                const unsigned jw = static_cast<unsigned>(j - wlo[k]);
-                good = good & certain & (jw < static_cast<unsigned>(wlen[k]));
-                wbin = wbin * wlen[k] + static_cast<int>(jw);
-              }
-              wb[u][e] = (good & live) ? wbin : -1;
-              side |= (!good & live) ? (1u << (4 * u + e)) : 0u;
-            }
-          }
-          // side path, one sample per trip (a lane rarely has more than one): certain and in range but
-          // outside the window -> global RED; everything else (uncertain, out of range, NaN) -> exact path
-          while (side) {
-            const int idx = __ffs(side) - 1;
-            side &= side - 1;
-            T x[KMAX]; WT wsel = WT(1);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (idx == 4 * u + e) {
-#pragma unroll
-                  for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
-                  wsel = wv[u][e];
-                }
-            bool sure = true; long long gbin = 0;
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-              int jx; const bool certain = uniform_guess<T>(p, k, x[k], jx);
-              sure = sure & certain & (static_cast<unsigned>(jx) < static_cast<unsigned>(p.nb[k]));
-              gbin = gbin * p.nb[k] + jx;
-            }
-            if (sure && !tiled) global_add(out_row, gbin, static_cast<double>(wsel));   // (tiling implies a full window)
-            else {
-              const int wbin = general_sample(x, static_cast<double>(wsel), out_row,
-                                              local_row(head + 4 * (g + static_cast<long long>(idx >> 2) * nthr) + (idx & 3)));
-              if (wbin >= 0) shared_add1(wbin, wsel, out_row);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const bool live = g + static_cast<long long>(u) * nthr < nvec;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              T x[KMAX];
-#pragma unroll
-              for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
-              wb[u][e] = live ? general_sample(x, static_cast<double>(wv[u][e]), out_row, local_row(head + 4 * (g + static_cast<long long>(u) * nthr) + e)) : -1;
-            }
-          }
-        }
-        if (W != 0 && fx) {
-          // fixed-point shared adds, straight-line: 4 low-limb ATOMS back to back, then the 4 high-limb REDs
-          // (each takes the carry from the value its ATOMS returned)
-          unsigned inexact = 0;
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            unsigned idx[4], lo[4], hi[4], old[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const WT vs = wv[u][e] * fx_mul;
-              const long long v = to_ll_rn(vs);
-              const bool exact = (static_cast<WT>(v) == vs) & (fabs(vs) < fx_limit);
-              const bool valid = wb[u][e] >= 0;
-              const bool ok = valid & exact;
-              inexact |= (valid & !exact) ? (1u << (4 * u + e)) : 0u;
-              idx[e] = ok ? static_cast<unsigned>(wb[u][e]) : trash;
-              lo[e] = ok ? static_cast<unsigned>(v) : 0u;
-              hi[e] = ok ? static_cast<unsigned>(static_cast<unsigned long long>(v) >> 32) : 0u;
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) old[e] = atoms_add_u32(sh_lo + 4u * idx[e], lo[e]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) reds_add_u32(sh_hi + 4u * idx[e], hi[e] + ((old[e] + lo[e] < old[e]) ? 1u : 0u));
-          }
-          if (inexact) {   // rare: weights that are not exact multiples of the scale -> float64 global RED
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (inexact & (1u << (4 * u + e))) global_add(out_row, window_to_global(wb[u][e]), static_cast<double>(wv[u][e]));
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < U; ++u) shared_add4(wb[u], wv[u], out_row);
-        }
-      }
-    }
-    s += len;
-
-    // ---- flush the shared histogram of this row segment and clear it
-    __syncthreads();
-    if (p.hist_mode != XHK_GLOBAL) {
-      const bool full = p.hist_mode == XHK_FULL;
-      const bool owned = full && p.store_owned_rows && c0 == 0 && len == p.N;
-      unsigned int* lo32 = reinterpret_cast<unsigned int*>(shist);
-      unsigned int* hi32 = lo32 + wcap;
-      for (int b = tid; b < wtot; b += nthr) {
-        OT v; bool nz;
-        if constexpr (W == 0) { v = static_cast<OT>(shist[b]); nz = v != 0; shist[b] = 0u; }
-        else if (fx) {
-          const long long iv = static_cast<long long>((static_cast<unsigned long long>(hi32[b]) << 32) | lo32[b]);
-          nz = iv != 0; v = static_cast<double>(iv) * fx_unmul;
-          lo32[b] = 0u; hi32[b] = 0u;
-        } else { v = shist[b]; nz = v != 0.0; shist[b] = 0.0; }
-        if (owned) out_row[b] = v;
-        else if (nz) atomicAdd(out_row + (full ? static_cast<long long>(b) : window_to_global(b)), v);
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// probe kernel: (1) marginal histograms of a strided probe of the block -> the densest hyper-rectangle
-// of at most `budget` bins (XHK_WINDOW); (2) the fixed-point scale of the weights.  One CTA, ~10-20 us;
-// run once per call when the bin space exceeds shared memory or weights are present.
-// ---------------------------------------------------------------------------------------------
-template <typename T, int KT>
-__global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant__ XhkParams p, XhkWindow* wout, int budget,
-                                                           int n_probe) {
-  constexpr int KMAX = KT ? KT : XHK_MAX_VARS;
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ int s_moff[XHK_MAX_VARS + 1];
-  __shared__ unsigned long long s_wmax;
-  __shared__ int s_fail, s_seen;
-  __shared__ double s_mul, s_limit;
-  const int K = KT ? KT : p.n_vars, tid = threadIdx.x, nthr = blockDim.x;
-  T* sedges = reinterpret_cast<T*>(smem);
-  const size_t edges_al = (static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15);
-  unsigned short* slut = reinterpret_cast<unsigned short*>(smem + edges_al);
-  unsigned int* marg = reinterpret_cast<unsigned int*>(smem + edges_al + ((static_cast<size_t>(p.n_lut_total) * 2 + 15) & ~static_cast<size_t>(15)));
-  for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
-  for (int i = tid; i < p.n_lut_total; i += nthr) slut[i] = p.lut[i];
-  if (tid == 0) { int o = 0; for (int k = 0; k < K; ++k) { s_moff[k] = o; o += p.nb[k]; } s_moff[K] = o; s_wmax = 0ull; s_fail = 0; s_seen = 0; }
-  __syncthreads();
-  const int mtot = s_moff[K];
-  for (int i = tid; i < mtot; i += nthr) marg[i] = 0u;
-  __syncthreads();
-  const long long total = p.M * p.N;
-  // probe positions: 256-sample contiguous runs spread evenly over the block (few pages touched: far-apart
-  // single-element probes cost ~100 us of TLB misses on multi-GB inputs)
-  const long long n_runs = (n_probe + 255) / 256;
-  const long long run_stride = total / n_runs;
-  auto probe_pos = [&](long long i) -> long long { return (i >> 8) * run_stride + (i & 255); };
-  const bool flat = p.M == 1;
-  auto locate = [&](long long pos, long long& r, long long& c) {
-    if (flat) { r = 0; c = pos; } else { r = pos / p.N; c = pos - r * p.N; }
-  };
-  auto wload = [&](long long r, long long c) -> double {
-    return p.w_dtype == 1 ? static_cast<double>((static_cast<const float*>(p.w) + r * p.wstride)[c])
-                          : (static_cast<const double*>(p.w) + r * p.wstride)[c];
-  };
-  constexpr int PB = 8;  // probe positions in flight per thread
-  unsigned long long wmx = 0ull;
-  double wkeep[PB]; int nkeep = 0;        // this thread's probe weights (first batch; enough for the statistic)
-  for (long long i0 = tid; i0 < n_probe; i0 += static_cast<long long>(PB) * nthr) {
-    T xs[PB][KMAX]; double ws[PB]; bool have[PB];
-#pragma unroll
-    for (int b = 0; b < PB; ++b) {
-      const long long i = i0 + static_cast<long long>(b) * nthr;
-      const long long pos = probe_pos(i);
-      have[b] = i < n_probe && pos < total;
-      ws[b] = 0.0;
-      if (have[b]) {
-        long long r, c; locate(pos, r, c);
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) if (k < K) xs[b][k] = (static_cast<const T*>(p.data[k]) + r * p.stride[k])[c];
-        if (p.w_dtype != 0) ws[b] = wload(r, c);
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < PB; ++b) {
-      if (have[b]) {
-        int j[KMAX]; bool ok = true;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) if (k < K) { j[k] = exact_bin_inline<T>(p, k, sedges, slut, xs[b][k]); ok = ok && j[k] >= 0; }
-        if (ok) {
-#pragma unroll
-          for (int k = 0; k < KMAX; ++k) if (k < K) atomicAdd(&marg[s_moff[k] + j[k]], 1u);
-        }
-        if (p.w_dtype != 0) {
-          const double a = fabs(ws[b]);
-          if (a < INFINITY) { const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(a)); if (bits > wmx) wmx = bits; }
-          if (i0 == tid) { wkeep[b] = ws[b]; nkeep = b + 1; }
-        }
-      }
-    }
-  }
-  if (p.w_dtype != 0) {   // non-negative doubles order like their bit patterns; one shared atomic per warp
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, wmx, o); if (t > wmx) wmx = t; }
-    if ((tid & 31) == 0) atomicMax(&s_wmax, wmx);
-  }
-  __syncthreads();
-  // ---- weights: scale from the largest finite probe weight; count the probe weights that would not be
-  //      exact at that scale; too many (> 1/64) -> float64 shared adds instead of fixed point
-  if (p.w_dtype != 0) {
-    if (tid == 0) {
-      const double m = __longlong_as_double(static_cast<long long>(s_wmax));
-      const int e = m > 0.0 ? ilogb(m) : 0;
-      const int sh = p.fx_vbits - 3 - e;          // v = w * 2^sh ; the largest probe weight maps below 2^(vbits-2)
-      s_mul = ldexp(1.0, sh); s_limit = ldexp(1.0, p.fx_vbits);
-      s_seen = (p.w_dtype == 1 && (sh > 100 || sh < -100)) ? -(1 << 30) : 0;   // outside fp32's exact power-of-two range
-    }
-    __syncthreads();
-    int fails = 0;
-#pragma unroll
-    for (int i = 0; i < PB; ++i) {
-      if (i < nkeep) {
-        const double vs = wkeep[i] * s_mul;
-        if (!((static_cast<double>(__double2ll_rn(vs)) == vs) & (fabs(vs) < s_limit))) ++fails;
-      }
-    }
-    int seen = nkeep;
-    for (int o = 16; o > 0; o >>= 1) { fails += __shfl_xor_sync(0xffffffffu, fails, o); seen += __shfl_xor_sync(0xffffffffu, seen, o); }
-    if ((tid & 31) == 0 && seen) { atomicAdd(&s_fail, fails); atomicAdd(&s_seen, seen); }
-    __syncthreads();
-    if (tid == 0) {
-      wout->fx_mul = s_mul; wout->fx_unmul = 1.0 / s_mul; wout->fx_limit = s_limit;
-      wout->fx_ok = (s_seen > 0 && static_cast<long long>(s_fail) * 64 <= s_seen) ? 1 : 0;
-    }
-  } else if (tid == 0) { wout->fx_ok = 0; wout->fx_mul = 0.0; wout->fx_unmul = 0.0; wout->fx_limit = 0.0; }
-
-  // ---- window: warp 0 bisects a density threshold (density of slice s of variable k = marg * nb_k, equal for
-  //      all slices of a uniform distribution); the box of variable k spans the slices at or above the
-  //      threshold.  Then lane 0 grows the box greedily while it fits the budget.
-  if (tid < 32) {
-    const unsigned full = 0xffffffffu;
-    auto box_at = [&](unsigned long long th, int* lo, int* len) -> long long {
-      long long vol = 1;
-      for (int k = 0; k < K; ++k) {
-        int first = 0x7fffffff, last = -1;
-        for (int s = tid; s < p.nb[k]; s += 32)
-          if (static_cast<unsigned long long>(marg[s_moff[k] + s]) * p.nb[k] >= th) { first = min(first, s); last = max(last, s); }
-        for (int o = 16; o > 0; o >>= 1) { first = min(first, __shfl_xor_sync(full, first, o)); last = max(last, __shfl_xor_sync(full, last, o)); }
-        if (last < 0) { first = 0; last = 0; }   // fixed up below (arg max)
-        lo[k] = first; len[k] = last - first + 1;
-        vol *= len[k]; if (vol > (1ll << 40)) vol = 1ll << 40;
-      }
-      return vol;
-    };
-    unsigned long long dmax = 0;
-    for (int k = 0; k < K; ++k)
-      for (int s = tid; s < p.nb[k]; s += 32) { const unsigned long long d = static_cast<unsigned long long>(marg[s_moff[k] + s]) * p.nb[k]; if (d > dmax) dmax = d; }
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(full, dmax, o); if (t > dmax) dmax = t; }
-    int lo[XHK_MAX_VARS], len[XHK_MAX_VARS];
-    unsigned long long tlo = 0, thi = dmax + 1;           // vol(tlo) > budget (unless everything fits), vol(thi) <= budget
-    if (box_at(0, lo, len) > budget) {
-      while (thi - tlo > 1) {
-        const unsigned long long mid = tlo + (thi - tlo) / 2;
-        if (box_at(mid, lo, len) <= budget) thi = mid; else tlo = mid;
-      }
-      long long vol = box_at(thi, lo, len);
-      if (tid == 0) {
-        // a variable with no slice at the threshold keeps its fullest slice
-        for (int k = 0; k < K; ++k) {
-          bool any = false;
-          for (int s = lo[k]; s < lo[k] + len[k]; ++s) any = any || static_cast<unsigned long long>(marg[s_moff[k] + s]) * p.nb[k] >= thi;
-          if (!any) { int arg = 0; unsigned best = 0; for (int s = 0; s < p.nb[k]; ++s) if (marg[s_moff[k] + s] > best) { best = marg[s_moff[k] + s]; arg = s; } lo[k] = arg; len[k] = 1; }
-        }
-        vol = 1; for (int k = 0; k < K; ++k) vol *= len[k];
-        while (vol > budget) {   // cannot happen for a consistent threshold; kept as a guard
-          int kb = 0; for (int k = 1; k < K; ++k) if (len[k] > len[kb]) kb = k;
-          len[kb] -= 1; vol = 1; for (int k = 0; k < K; ++k) vol *= len[k];
-        }
-        while (true) {           // greedy growth: neighbouring slice with the most probe mass per added bin
-          int bk = -1, bside = 0; double bgain = -1.0;
-          for (int k = 0; k < K; ++k) {
-            long long nv = 1; for (int q = 0; q < K; ++q) nv *= (q == k ? len[q] + 1 : len[q]);
-            if (nv > budget) continue;
-            if (lo[k] > 0) { const double g = (static_cast<double>(marg[s_moff[k] + lo[k] - 1]) + 1e-3) * len[k]; if (g > bgain) { bgain = g; bk = k; bside = -1; } }
-            if (lo[k] + len[k] < p.nb[k]) { const double g = (static_cast<double>(marg[s_moff[k] + lo[k] + len[k]]) + 1e-3) * len[k]; if (g > bgain) { bgain = g; bk = k; bside = 1; } }
-          }
-          if (bk < 0) break;
-          if (bside < 0) lo[bk] -= 1;
-          len[bk] += 1;
-        }
-      }
-    }
-    if (tid == 0)
-      for (int k = 0; k < XHK_MAX_VARS; ++k) { wout->lo[k] = k < K ? lo[k] : 0; wout->len[k] = k < K ? len[k] : 0; }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// column layout: reductions over LEADING axes.  The arrays are (n_outer, N, inner) C-contiguous blocks and the
-// histogram is taken over N for every (a, m).  One thread owns one kept column m: it walks down the reduced axis
-// (adjacent threads read adjacent addresses: coalesced) and accumulates into a thread-PRIVATE histogram
-// hist[bin][thread] in shared memory — plain read-modify-write, no atomics, conflict-free banks; weighted sums are
-// added in sample order like np.bincount.  The reference has to copy for this layout (np.moveaxis + reshape,
-// core.py:218-226).  grid = (n_outer * column tiles, nsplit slices of the reduced axis).
-// ---------------------------------------------------------------------------------------------
-template <typename T, int W, int KT>
-__global__ void __launch_bounds__(kMaxThreads, 1) k_hist_cols(const __grid_constant__ XhkParams p, long long inner, int tm, int accumulate) {
-  using HT = typename std::conditional<W == 0, unsigned int, double>::type;
-  using OT = typename std::conditional<W == 0, unsigned long long, double>::type;
-  using WT = typename WType<W>::type;
-  constexpr int KMAX = KT ? KT : XHK_MAX_VARS;
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int K = KT ? KT : p.n_vars;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  T* sedges = reinterpret_cast<T*>(smem);
-  const size_t edges_al = (static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15);
-  unsigned short* slut = reinterpret_cast<unsigned short*>(smem + edges_al);
-  HT* hist = reinterpret_cast<HT*>(smem + edges_al + ((static_cast<size_t>(p.n_lut_total) * 2 + 15) & ~static_cast<size_t>(15)));
-  for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
-  for (int i = tid; i < p.n_lut_total; i += nthr) slut[i] = p.lut[i];
-  const int B = static_cast<int>(p.B);
-  for (int i = tid; i < B * tm; i += nthr) hist[i] = HT(0);
-  __syncthreads();
-
-  const long long tiles = (inner + tm - 1) / tm;
-  const long long a = blockIdx.x / tiles;
-  const long long m0 = (blockIdx.x - a * tiles) * tm;
-  const long long m = m0 + tid;
-  const long long N = p.N;
-  const long long n0 = N * blockIdx.y / gridDim.y, n1 = N * (blockIdx.y + 1ll) / gridDim.y;
-  if (tid < tm && m < inner) {
-    const T* px[KMAX];
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) px[k] = (k < K) ? static_cast<const T*>(p.data[k]) + a * N * inner + m : nullptr;
-    const WT* pw = (W != 0) ? static_cast<const WT*>(p.w) + a * N * inner + m : nullptr;
-    auto one = [&](const T (&x)[KMAX], WT wv) {
-      int bin = 0; bool ok = true;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (k < K) {
-          const int j = exact_bin_inline<T>(p, k, sedges, slut, x[k]);
-          ok = ok && j >= 0;
-          bin = bin * p.nb[k] + j;
-        }
-      }
-      if (ok) {
-        HT* h = hist + static_cast<size_t>(bin) * tm + tid;
-        if constexpr (W == 0) *h += 1u; else *h += static_cast<double>(wv);
-      }
-    };
-    // rows of the reduced axis in flight per thread (4-byte loads: keep ~32 B per thread outstanding)
-    constexpr int UN = (sizeof(T) * KMAX + (W == 0 ? 0 : sizeof(WT)) <= 8) ? 8 : 4;
-    long long n = n0;
-    for (; n + UN <= n1; n += UN) {
-      T xv[UN][KMAX]; WT wv[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) if (k < K) xv[u][k] = __ldcs(px[k] + (n + u) * inner);
-        wv[u] = WT(1);
-        if constexpr (W != 0) wv[u] = __ldcs(pw + (n + u) * inner);
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) one(xv[u], wv[u]);
-    }
-    for (; n < n1; ++n) {
-      T x[KMAX]; WT wv = WT(1);
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) if (k < K) x[k] = px[k][n * inner];
-      if constexpr (W != 0) wv = pw[n * inner];
-      one(x, wv);
-    }
-  }
-  __syncthreads();
-  // flush: consecutive threads write consecutive bins of one output row (coalesced); out row = a*inner + m
-  OT* out = static_cast<OT*>(p.out) + (a * inner + m0) * B;
-  const long long cols = (inner - m0 < tm) ? inner - m0 : tm;
-  for (long long i = tid; i < cols * B; i += nthr) {
-    const int ml = static_cast<int>(i / B), b = static_cast<int>(i - static_cast<long long>(ml) * B);
-    const HT v = hist[static_cast<size_t>(b) * tm + ml];
-    if (accumulate) { if (v != HT(0)) atomicAdd(out + i, static_cast<OT>(v)); }
-    else out[i] = static_cast<OT>(v);
-  }
-}
-
-typedef void (*ColsKernel)(const XhkParams, long long, int, int);
-template <typename T, int W>
-ColsKernel pick_cols_k(int K) {
-  switch (K) {
-    case 1: return k_hist_cols<T, W, 1>;
-    case 2: return k_hist_cols<T, W, 2>;
-    case 3: return k_hist_cols<T, W, 3>;
-    case 4: return k_hist_cols<T, W, 4>;
-    default: return k_hist_cols<T, W, 0>;
-  }
-}
-template <typename T>
-ColsKernel pick_cols_w(int w, int K) { return w == 0 ? pick_cols_k<T, 0>(K) : w == 1 ? pick_cols_k<T, 1>(K) : pick_cols_k<T, 2>(K); }
-ColsKernel pick_cols(int dtype, int w, int K) {
-  return dtype == 1 ? pick_cols_w<float>(w, K) : dtype == 2 ? pick_cols_w<double>(w, K) : pick_cols_w<long long>(w, K);
-}
 
 // zero the rows of `out` that are shared between CTAs under the sample partition (XHK_FULL only)
 template <typename OT>
@@ -906,42 +93,14 @@ __global__ void k_flush(uint4* buf, size_t n16) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) buf[i] = make_uint4(i, 0, 0, 0);
 }
 
-// ---------------------------------------------------------------------------------------------
-// dispatch
-// ---------------------------------------------------------------------------------------------
-typedef void (*HistKernel)(const XhkParams);
-
-template <typename T, int W, int MODE>
-HistKernel pick_k(int K) {
-  switch (K) {
-    case 1: return k_hist<T, W, 1, MODE>;
-    case 2: return k_hist<T, W, 2, MODE>;
-    case 3: return k_hist<T, W, 3, MODE>;
-    case 4: return k_hist<T, W, 4, MODE>;
-    default: return k_hist<T, W, 0, 0>;
-  }
+XhkHistKernel pick(int dtype, int w_dtype, int K, int mode) {
+  return dtype == 1 ? xhk_pick_hist_f32(w_dtype, K, mode) : dtype == 2 ? xhk_pick_hist_f64(w_dtype, K, mode) : xhk_pick_hist_i64(w_dtype, K, mode);
 }
-template <typename T, int W>
-HistKernel pick_m(int K, int mode) {
-  if (mode == 1) return pick_k<T, W, 1>(K);
-  if (mode == 2) return pick_k<T, W, 2>(K);
-  return pick_k<T, W, 0>(K);
+XhkWindowKernel pick_window(int dtype, int K) {
+  return dtype == 1 ? xhk_pick_window_f32(K) : dtype == 2 ? xhk_pick_window_f64(K) : xhk_pick_window_i64(K);
 }
-
-HistKernel pick(int dtype, int w_dtype, int K, int mode) {
-  if (dtype == 3) {   // int64 data: general kernel only
-    if (w_dtype == 0) return pick_k<long long, 0, 0>(K);
-    if (w_dtype == 1) return pick_k<long long, 1, 0>(K);
-    return pick_k<long long, 2, 0>(K);
-  }
-  if (dtype == 1) {
-    if (w_dtype == 0) return pick_m<float, 0>(K, mode);
-    if (w_dtype == 1) return pick_m<float, 1>(K, mode);
-    return pick_m<float, 2>(K, mode);
-  }
-  if (w_dtype == 0) return pick_m<double, 0>(K, mode);
-  if (w_dtype == 1) return pick_m<double, 1>(K, mode);
-  return pick_m<double, 2>(K, mode);
+XhkColsKernel pick_cols(int dtype, int w, int K) {
+  return dtype == 1 ? xhk_pick_cols_f32(w, K) : dtype == 2 ? xhk_pick_cols_f64(w, K) : xhk_pick_cols_i64(w, K);
 }
 
 // Mode 2 keeps 4 samples x K variables of bins live; with 3+ fp64 variables that spills under the 64-register
@@ -953,22 +112,9 @@ int kernel_mode(const XhkParams& p, int dtype) {
   return (p.all_branch_free && rec <= 16) ? 2 : 0;
 }
 
-typedef void (*WindowKernel)(const XhkParams, XhkWindow*, int, int);
-template <typename T>
-WindowKernel pick_window_t(int K) {
-  switch (K) {
-    case 1: return k_window<T, 1>;
-    case 2: return k_window<T, 2>;
-    case 3: return k_window<T, 3>;
-    case 4: return k_window<T, 4>;
-    default: return k_window<T, 0>;
-  }
-}
-WindowKernel pick_window(int dtype, int K) {
-  return dtype == 1 ? pick_window_t<float>(K) : dtype == 2 ? pick_window_t<double>(K) : pick_window_t<long long>(K);
-}
 
 }  // namespace
+
 
 cudaError_t xhk_set_smem_limits(int max_optin) {
   for (int dt = 1; dt <= 3; ++dt)
@@ -994,7 +140,7 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
 }
 
 cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l) {
-  HistKernel k = pick(l.dtype, l.w_dtype, p.n_vars, kernel_mode(p, l.dtype));
+  XhkHistKernel k = pick(l.dtype, l.w_dtype, p.n_vars, kernel_mode(p, l.dtype));
   k<<<l.grid, l.threads, l.smem_bytes, l.stream>>>(p);
   return cudaGetLastError();
 }
@@ -1015,7 +161,7 @@ size_t xhk_window_kernel_smem(const XhkParams& p) {
 
 cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow* window_dev, int budget_bins, int n_probe) {
   const size_t smem = xhk_window_kernel_smem(p);
-  pick_window(l.dtype, p.n_vars)<<<1, kMaxThreads, smem, l.stream>>>(p, window_dev, budget_bins, n_probe);
+  pick_window(l.dtype, p.n_vars)<<<1, XHK_THREADS, smem, l.stream>>>(p, window_dev, budget_bins, n_probe);
   return cudaGetLastError();
 }
 

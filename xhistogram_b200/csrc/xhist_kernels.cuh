@@ -97,6 +97,18 @@ struct XhkLaunch {
   cudaStream_t stream;
 };
 
+// kernel entry points by data type (defined in xhist_k_f32.cu / xhist_k_f64.cu / xhist_k_i64.cu)
+typedef void (*XhkHistKernel)(const XhkParams);
+typedef void (*XhkWindowKernel)(const XhkParams, XhkWindow*, int, int);
+typedef void (*XhkColsKernel)(const XhkParams, long long, int, int);
+#define XHK_DECLARE_PICKERS(DT)                                  \
+  XhkHistKernel xhk_pick_hist_##DT(int w, int K, int mode);      \
+  XhkWindowKernel xhk_pick_window_##DT(int K);                   \
+  XhkColsKernel xhk_pick_cols_##DT(int w, int K);
+XHK_DECLARE_PICKERS(f32)
+XHK_DECLARE_PICKERS(f64)
+XHK_DECLARE_PICKERS(i64)
+
 // host-callable launchers (defined in xhist_kernels.cu)
 cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l);
 // column layout: p.M = n_outer * n_inner logical rows, p.N reduced length, inner = n_inner; tm columns per CTA,

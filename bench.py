@@ -379,7 +379,7 @@ def main():
                    "accumulate": "float64 (np.bincount semantics), fp32 compare on round-up edges"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * n * 12, "d2h_bytes_per_step": world * NBINS * NBINS * 8,
                 "steps": e2e_steps, "matches_device_result": e2e_ok},
-        "gpu_launches": args.steps * 2 * world,
+        "gpu_launches": args.steps * 3 * world,   # probe + the two sibling k_hist launches (one of them returns at once)
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,

@@ -50,6 +50,7 @@ typedef enum xh_mem { XH_HOST = 0, XH_DEVICE = 1 } xh_mem;
 #define XH_FLAG_FORCE_GLOBAL 2u /* testing: bypass the shared-memory histogram, global atomics only         */
 #define XH_FLAG_FORCE_SEARCH 4u /* testing: bypass the uniform-edge fast path, binary search only           */
 #define XH_FLAG_FORCE_WINDOW 8u /* testing: use the windowed shared-memory histogram even if all bins fit   */
+#define XH_FLAG_NO_FX32 16u     /* testing: fp32 weights never take the one-limb (4 bytes per bin) accumulation  */
 
 /*
  * One histogram request over a logical (n_rows, n_cols) block: histogram along the

@@ -52,7 +52,9 @@ def assert_hist_equal(got, want, rtol=1e-6):
         assert np.array_equal(got, want)
         return
     assert np.array_equal(np.isnan(got), np.isnan(want))
-    m = ~np.isnan(want)
+    inf = np.isinf(want)
+    assert np.array_equal(got[inf], want[inf])            # infinite sums (inf weights) must match in sign
+    m = np.isfinite(want)
     scale = np.maximum(np.abs(want[m]), np.finfo(np.float64).tiny)
     err = np.abs(got[m] - want[m]) / scale
     assert err.size == 0 or err.max() <= rtol, float(err.max())

@@ -17,6 +17,7 @@ PATHS = {
     "search_only": _cabi.XH_FLAG_FORCE_SEARCH,
     "windowed": _cabi.XH_FLAG_FORCE_WINDOW,
     "windowed_search": _cabi.XH_FLAG_FORCE_WINDOW | _cabi.XH_FLAG_FORCE_SEARCH,
+    "no_fx32": _cabi.XH_FLAG_NO_FX32,
 }
 
 
@@ -72,6 +73,47 @@ def test_random_problems_match_oracle(seed):
         with core.debug_flags(PATHS[path]):
             h, _ = core.histogram(*args, bins=edges, axis=-1, weights=w)
         assert_hist_equal(h, want, rtol=1e-6)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("layout", ["flat", "rows", "short_rows"])
+def test_fx32_weights(k, dtype, layout):
+    """fp32 weights that are multiples of 2**-24 take the one-limb accumulation (k_hist<W=3>); planted weights that
+    do not fit it (negative, NaN, inf, huge, finer than the scale) must leave through the exact global path."""
+    r = np.random.default_rng(77 + k)
+    shape = {"flat": (1, 600_000), "rows": (7, 90_001), "short_rows": (3000, 60)}[layout]
+    args = [r.standard_normal(shape).astype(dtype) for _ in range(k)]
+    nb = {1: 1000, 2: 300, 3: 40}[k]
+    edges = [np.linspace(-3, 3, nb + 1)] + [np.sort(r.uniform(-3, 3, nb // 2 + 1)) for _ in range(k - 1)]
+    w = r.random(shape, dtype=np.float32)
+    flat = w.reshape(-1)
+    idx = r.choice(flat.size, 64, replace=False)
+    flat[idx] = np.resize(np.array([-0.5, np.nan, np.inf, 3.0e6, 1e-30, 0.0, -0.0, 1.75, 2.5, 0.3, -np.inf, 2.0 ** -30],
+                                   dtype=np.float32), 64)
+    want = O.block_bincount(args, edges, w)
+    got = {}
+    for path in ("default", "windowed", "no_fx32", "global_atomics"):
+        with core.debug_flags(PATHS[path]):
+            got[path], _ = core.histogram(*args, bins=edges, axis=-1, weights=w)
+        assert_hist_equal(got[path], want, rtol=1e-6)
+    if layout == "flat":   # also from device memory
+        h, _ = core.histogram(*[DeviceArray.from_numpy(a.reshape(-1)) for a in args], bins=edges,
+                              weights=DeviceArray.from_numpy(w.reshape(-1)))
+        assert_hist_equal(h, want[0], rtol=1e-6)
+
+
+def test_fx32_limb_wraps_are_exact():
+    """Every sample in ONE bin with weights just below 1: the u32 limb wraps every ~256 adds; the sum stays exact."""
+    n = 3_000_000
+    x = np.full(n, 0.25, dtype=np.float32)
+    w = np.full(n, 1.0 - 2.0 ** -24, dtype=np.float32)
+    w[::3] = 0.5
+    e = np.linspace(0, 1, 11)
+    h, _ = core.histogram(x, bins=e, weights=w)
+    want = np.zeros(10)
+    want[2] = w.astype(np.float64).sum()      # exact in float64
+    assert np.array_equal(h, want)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -133,6 +175,9 @@ def test_cfg3_shape_slab_and_invariants():
     with core.debug_flags(PATHS["global_atomics"]):
         hg, _ = core.histogram(x, y, bins=[e, e], weights=w)
     assert np.array_equal(hg, hw)
+    with core.debug_flags(PATHS["no_fx32"]):          # two-limb accumulation instead of the one-limb form
+        h64, _ = core.histogram(x, y, bins=[e, e], weights=w)
+    assert np.array_equal(h64, hw)
     # marginal of the joint histogram equals the 1-D histogram
     hx, _ = core.histogram(x, bins=e)
     inr = core.histogram(y, bins=np.array([-4.0, 4.0]))[0][0]

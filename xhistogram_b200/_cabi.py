@@ -18,6 +18,7 @@ XH_FLAG_NO_ZERO = 1
 XH_FLAG_FORCE_GLOBAL = 2
 XH_FLAG_FORCE_SEARCH = 4
 XH_FLAG_FORCE_WINDOW = 8
+XH_FLAG_NO_FX32 = 16
 XH_NCCL_UNIQUE_ID_BYTES = 128
 
 _ERRORS = {

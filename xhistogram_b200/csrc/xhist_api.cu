@@ -130,7 +130,7 @@ int get_ctx(int device, Ctx** out) {
   for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&c->copied[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->consumed[i], cudaEventDisableTiming)); }
   CU(cudaMalloc(&c->window, sizeof(XhkWindow)));
   CU(cudaMalloc(&c->minmax, 296 * 3 * sizeof(double)));
-  CU(xhk_set_smem_limits(c->smem_optin - 64));  // 64 B of static shared memory in k_hist
+  CU(xhk_set_smem_limits(c->smem_optin - XHK_STATIC_SMEM));  // static shared memory of k_hist
   g_ctx[device] = c;
   *out = c;
   return XH_OK;
@@ -326,7 +326,9 @@ int upload_edges(Ctx* c, const Prep& pr, cudaStream_t s) {
 }
 
 // Launch plan of one block whose data/weights/out pointers are DEVICE pointers.
-int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Plan& pl, int tile_rows = 1, long long tile_n = 0) {
+// fx32 = true plans the k_hist<W = 3> sibling of an fp32-weighted block (4 bytes per shared bin instead of 8).
+int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Plan& pl, int tile_rows = 1, long long tile_n = 0,
+               bool fx32 = false) {
   XhkParams& p = pl.p;
   p = pr.base;
   p.tile_rows = tile_rows; p.tile_n = static_cast<int>(tile_n); p.tile_magic = 1; p.tile_shift = 0;
@@ -349,8 +351,8 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
 
   // shared-memory budget
   const size_t edges_al = pr.edges_al;
-  const size_t item = d->w_dtype == XH_NONE ? 4 : 8;
-  const long long budget1 = static_cast<long long>(c->smem_optin) - 64 - static_cast<long long>(edges_al);  // 1 CTA / SM
+  const size_t item = (d->w_dtype == XH_NONE || fx32) ? 4 : 8;
+  const long long budget1 = static_cast<long long>(c->smem_optin) - XHK_STATIC_SMEM - static_cast<long long>(edges_al);  // 1 CTA / SM
   if (budget1 < 0) return fail(XH_ERR_UNSUPPORTED, "bin edges (%zu bytes) do not fit in shared memory", pr.edge_host.size());
   const long long cap1 = budget1 / static_cast<long long>(item) - 32;   // 32 trash slots (see k_hist)
   int mode;
@@ -366,7 +368,7 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
   if (mode == XHK_FULL) {
     smem = edges_al + static_cast<size_t>(B + 32) * item;
     // two 512-thread CTAs per SM when both histograms fit (a flush of one overlaps the stream of the other)
-    if (2 * (smem + 1024 + 64) <= static_cast<size_t>(c->smem_per_sm)) { ctas_per_sm = 2; threads = XHK_THREADS / 2; }
+    if (2 * (smem + 1024 + XHK_STATIC_SMEM) <= static_cast<size_t>(c->smem_per_sm)) { ctas_per_sm = 2; threads = XHK_THREADS / 2; }
     p.hist_capacity = static_cast<int>(B);
   } else if (mode == XHK_WINDOW) {
     long long cap = cap1;
@@ -406,24 +408,52 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
   if (no_zero) pl.zero = Plan::ZERO_NONE;
   else if (p.store_owned_rows) pl.zero = (p.partition == XHK_PART_ROWS) ? Plan::ZERO_NONE : Plan::ZERO_SHARED;
   else pl.zero = Plan::ZERO_ALL;
-  pl.l.dtype = d->dtype; pl.l.w_dtype = d->w_dtype; pl.l.grid = grid; pl.l.threads = threads; pl.l.smem_bytes = smem; pl.l.stream = stream;
+  pl.l.dtype = d->dtype; pl.l.w_dtype = fx32 ? 3 : d->w_dtype; pl.l.grid = grid; pl.l.threads = threads; pl.l.smem_bytes = smem; pl.l.stream = stream;
   return XH_OK;
 }
 
-// Enqueue zero-fill, window selection and the histogram kernel of one planned block.
-int enqueue(Ctx* c, const Prep& pr, Plan& pl) {
+// Enqueue zero-fill, window selection and the histogram kernel(s) of one planned block.  With an fx32 sibling
+// plan both kernels are launched; the probe's verdict (XhkWindow::fx_mode, read on the device) makes exactly one
+// of them do the work, so the zero-fill has to suit either.
+int enqueue(Ctx* c, const Prep& pr, Plan& pl, Plan* sib = nullptr) {
   cudaStream_t s = pl.l.stream;
   const size_t osz = 8;
+  if (sib) {
+    pl.p.fx32_sibling = 1;
+    const bool same = sib->zero == pl.zero &&
+                      (pl.zero != Plan::ZERO_SHARED || (sib->l.grid == pl.l.grid && sib->p.per_cta == pl.p.per_cta));
+    if (!same) pl.zero = Plan::ZERO_ALL;
+  }
   if (pl.zero == Plan::ZERO_ALL) CU(cudaMemsetAsync(pl.p.out, 0, static_cast<size_t>(pl.p.M) * pl.p.B * osz, s));
   else if (pl.zero == Plan::ZERO_SHARED) CU(xhk_launch_zero_shared_rows(pl.p, pl.l));
   if (pl.need_window && !pr.window_done) {
     const long long total = pl.p.M * pl.p.N;
     const int n_probe = static_cast<int>(std::min<long long>(total, 1 << 13));
-    CU(xhk_launch_window(pl.p, pl.l, c->window, pl.window_budget, n_probe));
+    CU(xhk_launch_window(pl.p, pl.l, c->window, pl.window_budget, sib ? sib->window_budget : 0, n_probe));
     pr.window_done = true;
   }
+  if (sib) CU(xhk_launch_hist(sib->p, sib->l));
   CU(xhk_launch_hist(pl.p, pl.l));
   return XH_OK;
+}
+
+// Plan a block and, for fp32 weights, its fx32 sibling; enqueue both.
+int plan_and_enqueue(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, int tile_rows = 1, long long tile_n = 0) {
+  Plan pl;
+  int rc = plan_block(c, pr, d, stream, pl, tile_rows, tile_n);
+  if (rc) return rc;
+  Plan sib;
+  // The one-limb form pays off through its larger window, i.e. when the 8-byte bins do not all fit; when they do,
+  // the two-limb form has no spills and no wraps.  Wraps reach the output through global adds, so the sibling
+  // never writes rows with plain stores (a windowed main plan zero-fills the whole output anyway).
+  bool have_sib = d->w_dtype == XH_F32 && d->dtype != XH_I64 && pl.p.hist_mode == XHK_WINDOW && !(d->flags & XH_FLAG_NO_FX32);
+  if (have_sib) {
+    rc = plan_block(c, pr, d, stream, sib, tile_rows, tile_n, true);
+    if (rc) return rc;
+    have_sib = sib.p.hist_mode != XHK_GLOBAL && sib.need_window;
+    sib.p.store_owned_rows = 0;
+  }
+  return enqueue(c, pr, pl, have_sib ? &sib : nullptr);
 }
 
 int validate(const xh_desc* d) {
@@ -469,7 +499,7 @@ int choose_tile_rows(Ctx* c, const Prep& pr, const xh_desc* d) {
   for (int k = 0; k < d->n_vars; ++k) if (d->row_stride[k] != N) return 1;   // contiguous rows only
   if (d->weights && d->w_row_stride != N) return 1;
   const long long item = d->w_dtype == XH_NONE ? 4 : 8;
-  const long long per_cta = (static_cast<long long>(c->smem_per_sm) / 2 - 1024 - 64 - static_cast<long long>(pr.edges_al)) / item - 32;
+  const long long per_cta = (static_cast<long long>(c->smem_per_sm) / 2 - 1024 - XHK_STATIC_SMEM - static_cast<long long>(pr.edges_al)) / item - 32;
   const long long r_max = std::min<long long>(per_cta / std::max<long long>(B, 1), M);
   const long long target = 16384;
   long long R = std::min<long long>(r_max, (target + N - 1) / N);
@@ -486,10 +516,7 @@ int run_device_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stre
     t.n_rows = tiles; t.n_cols = static_cast<long long>(R) * N;
     for (int k = 0; k < d->n_vars; ++k) t.row_stride[k] = t.n_cols;
     if (d->weights) t.w_row_stride = t.n_cols;
-    Plan pl;
-    int rc = plan_block(c, pr, &t, stream, pl, R, N);
-    if (rc) return rc;
-    rc = enqueue(c, pr, pl);
+    int rc = plan_and_enqueue(c, pr, &t, stream, R, N);
     if (rc || rem == 0) return rc;
     xh_desc r = *d;                                  // the last M % R rows
     r.n_rows = rem;
@@ -498,10 +525,7 @@ int run_device_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stre
     r.out = static_cast<unsigned char*>(d->out) + static_cast<size_t>(tiles) * R * pr.base.B * 8;
     return run_device_block(c, pr, &r, stream);
   }
-  Plan pl;
-  int rc = plan_block(c, pr, d, stream, pl);
-  if (rc) return rc;
-  return enqueue(c, pr, pl);
+  return plan_and_enqueue(c, pr, d, stream);
 }
 
 // host inputs: double-buffered H2D pipeline feeding device blocks that accumulate into dev_out
@@ -585,7 +609,7 @@ int run_host_pipeline(Ctx* c, const Prep& pr, const xh_desc* d, void* dev_out) {
 int cols_tile(Ctx* c, const Prep& pr, const xh_desc* d, int* tm_out, size_t* smem_out) {
   const long long B = pr.base.B;
   const size_t item = d->w_dtype == XH_NONE ? 4 : 8;
-  const long long budget = static_cast<long long>(c->smem_optin) - 64 - static_cast<long long>(pr.edges_al);
+  const long long budget = static_cast<long long>(c->smem_optin) - XHK_STATIC_SMEM - static_cast<long long>(pr.edges_al);
   long long tm = budget / static_cast<long long>(B * item);
   tm = std::min<long long>(tm / 32 * 32, XHK_THREADS);
   if (tm < 32) return fail(XH_ERR_UNSUPPORTED, "column layout: %lld bins per column do not fit a per-thread shared histogram", B);

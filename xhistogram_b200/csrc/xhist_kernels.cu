@@ -118,7 +118,7 @@ int kernel_mode(const XhkParams& p, int dtype) {
 
 cudaError_t xhk_set_smem_limits(int max_optin) {
   for (int dt = 1; dt <= 3; ++dt)
-    for (int w = 0; w <= 2; ++w)
+    for (int w = 0; w <= (dt == 3 ? 2 : 3); ++w)
       for (int k = 1; k <= 5; ++k)
         for (int f = 0; f <= 2; ++f) {
           cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick(dt, w, k, f)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
@@ -159,9 +159,9 @@ size_t xhk_window_kernel_smem(const XhkParams& p) {
   return e + m;
 }
 
-cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow* window_dev, int budget_bins, int n_probe) {
+cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow* window_dev, int budget_bins, int budget32_bins, int n_probe) {
   const size_t smem = xhk_window_kernel_smem(p);
-  pick_window(l.dtype, p.n_vars)<<<1, XHK_THREADS, smem, l.stream>>>(p, window_dev, budget_bins, n_probe);
+  pick_window(l.dtype, p.n_vars)<<<1, XHK_THREADS, smem, l.stream>>>(p, window_dev, budget_bins, budget32_bins, n_probe);
   return cudaGetLastError();
 }
 

@@ -9,6 +9,8 @@
 #ifndef XHK_THREADS
 #define XHK_THREADS 1024
 #endif
+// static shared memory of k_hist (window geometry + flags), rounded up; the host subtracts it from the dynamic budget
+#define XHK_STATIC_SMEM 80
 enum { XHK_C_LO = 0, XHK_C_HI = 1, XHK_C_E0 = 2, XHK_C_INV = 3, XHK_C_DELTA = 4, XHK_C_OMD = 5 };
 
 // How the per-CTA shared-memory histogram is used.
@@ -33,7 +35,9 @@ struct XhkWindow {
   // below fx_limit; anything else goes to a float64 global RED.  fx_ok = 0 -> float64 shared adds instead.
   double fx_mul, fx_unmul, fx_limit;
   int fx_ok;
-  int pad;
+  // 64: two u32 limbs per bin (k_hist<W = 1 or 2>);  32: one u32 limb per bin, wraps go to the float64 output
+  // (k_hist<W = 3>, fp32 weights that are non-negative multiples of a power of two within 25 bits);  0: float64 adds
+  int fx_mode;
 };
 
 // Kernel parameters (passed by value, lives in the constant bank).
@@ -87,11 +91,13 @@ struct XhkParams {
   int tile_n;                       // samples of one real row
   unsigned tile_magic; int tile_shift;   // q = (umulhi(n, magic) + n) >> shift == n / tile_n for n < 2^31
   int fx_vbits;                     // fixed point: |v| < 2^fx_vbits keeps every per-flush bin sum below 2^63
+  int fx32_sibling;                 // 1: a k_hist<W = 3> launch of the same block precedes this one and does the work
+                                    //    when the probe chose fx_mode 32 (this launch then returns at once)
 };
 
 struct XhkLaunch {
   int dtype;       // 1 f32, 2 f64, 3 int64 (xh_dtype)
-  int w_dtype;     // 0 none, 1 f32, 2 f64
+  int w_dtype;     // 0 none, 1 f32, 2 f64, 3 f32 accumulated in one u32 limb per bin (fx32 sibling)
   int grid, threads;
   size_t smem_bytes;
   cudaStream_t stream;
@@ -99,7 +105,7 @@ struct XhkLaunch {
 
 // kernel entry points by data type (defined in xhist_k_f32.cu / xhist_k_f64.cu / xhist_k_i64.cu)
 typedef void (*XhkHistKernel)(const XhkParams);
-typedef void (*XhkWindowKernel)(const XhkParams, XhkWindow*, int, int);
+typedef void (*XhkWindowKernel)(const XhkParams, XhkWindow*, int, int, int);
 typedef void (*XhkColsKernel)(const XhkParams, long long, int, int);
 #define XHK_DECLARE_PICKERS(DT)                                  \
   XhkHistKernel xhk_pick_hist_##DT(int w, int K, int mode);      \
@@ -114,7 +120,7 @@ cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l);
 // column layout: p.M = n_outer * n_inner logical rows, p.N reduced length, inner = n_inner; tm columns per CTA,
 // nsplit CTAs share the reduced axis of one column tile (nsplit > 1 -> atomic flush into a zeroed out)
 cudaError_t xhk_launch_hist_cols(const XhkParams& p, const XhkLaunch& l, long long inner, int tm, int nsplit, int accumulate);
-cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow* window_dev, int budget_bins, int n_probe);
+cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow* window_dev, int budget_bins, int budget32_bins, int n_probe);
 cudaError_t xhk_launch_zero_shared_rows(const XhkParams& p, const XhkLaunch& l);
 cudaError_t xhk_set_smem_limits(int max_optin);
 cudaError_t xhk_launch_fill(void* ptr, int dtype, long long n, unsigned long long seed, long long offset, int normal, cudaStream_t s);

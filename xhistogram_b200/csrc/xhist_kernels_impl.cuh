@@ -133,12 +133,13 @@ __device__ __forceinline__ void load4(const double* p, long long g, double (&v)[
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
-template <int W> struct WType { using type = float; };
+template <int W> struct WType { using type = float; };   // W = 1 and W = 3: fp32 weights
 template <> struct WType<2> { using type = double; };
 
 // ---------------------------------------------------------------------------------------------
 // the histogram kernel
-//   T    : data type (float / double)        W : 0 no weights, 1 fp32 weights, 2 fp64 weights
+//   T    : data type (float / double)        W : 0 no weights, 1 fp32 weights, 2 fp64 weights,
+//                                                3 fp32 weights accumulated as ONE u32 limb per bin (fx32, see below)
 //   KT   : number of variables at compile time (1..4), or 0 = runtime p.n_vars (scalar loads only)
 //   MODE : 0 general (per-sample exact classification: range test, uniform guess / table-bracketed search)
 //          1 every variable has evenly spaced edges -> branch-free arithmetic classification of 8 samples at a
@@ -149,12 +150,20 @@ template <> struct WType<2> { using type = double; };
 template <typename T, int W, int KT, int MODE>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__ XhkParams p) {
   constexpr bool FAST = (MODE == 1);
-  using HT = typename std::conditional<W == 0, unsigned int, double>::type;          // shared accumulator
-  using OT = typename std::conditional<W == 0, unsigned long long, double>::type;    // global accumulator
+  using HT = typename std::conditional<W == 0 || W == 3, unsigned int, double>::type;   // shared accumulator
+  using OT = typename std::conditional<W == 0, unsigned long long, double>::type;       // global accumulator
   using WT = typename WType<W>::type;
   constexpr int KMAX = KT ? KT : XHK_MAX_VARS;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_wlo[XHK_MAX_VARS], s_wlen[XHK_MAX_VARS];
+  __shared__ int s_redo;   // fixed point, row owned by this CTA: a weight did not fit -> redo the segment with float64 adds
+  // fp32 weights are served by two sibling launches; the probe kernel's verdict (XhkWindow::fx_mode) decides which of
+  // them does the work, the other one returns at once (no host round trip between probe and histogram):
+  //   W == 3 (fx32): 4 bytes per bin — twice the shared window of the 8-byte forms — when (nearly) all weights are
+  //                  non-negative multiples of a common power of two spanning <= 25 bits (e.g. k * 2^-24 in [0, 1))
+  //   W == 1       : everything else (two u32 limbs, or float64 shared adds)
+  if constexpr (W == 3) { if (p.window->fx_mode != 32) return; }
+  if constexpr (W == 1) { if (p.fx32_sibling && p.window->fx_mode == 32) return; }
 
   const int K = KT ? KT : p.n_vars;
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -173,6 +182,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
     }
     s_wlo[tid] = lo; s_wlen[tid] = len;
   }
+  if (tid == 0) s_redo = 0;
   __syncthreads();
   int wlo[KMAX], wlen[KMAX];
   int wtot = (p.hist_mode == XHK_GLOBAL) ? 0 : 1;
@@ -184,12 +194,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   // obtained for free by seeding the Horner evaluation of the joint bin with the local row
   const bool tiled = p.tile_rows > 1;
   wtot *= p.tile_rows;
-  for (int i = tid; i < (W == 0 ? wtot : wtot + 32); i += nthr) shist[i] = HT(0);
+  for (int i = tid; i < (W == 0 ? wtot : wtot + 32); i += nthr) shist[i] = HT(0);   // (+ the trash slots)
   // weighted accumulation mode (uniform for the launch): exact fixed point in two u32 limbs, or float64 adds
-  bool fx = false; WT fx_mul = WT(0), fx_limit = WT(0); double fx_unmul = 0.0;
+  // `fx` can fall back to float64 adds for one row segment (see s_redo), hence not const
+  bool fx = false, fx_launch = false; WT fx_mul = WT(0), fx_limit = WT(0); double fx_unmul = 0.0, fx_carry = 0.0;
+  bool owned = false;      // the current row segment is a whole row that only this CTA touches: flushed with plain stores
   if constexpr (W != 0) {
     if (p.hist_mode != XHK_GLOBAL && p.window->fx_ok) {
-      fx = true; fx_mul = static_cast<WT>(p.window->fx_mul); fx_limit = static_cast<WT>(p.window->fx_limit); fx_unmul = p.window->fx_unmul;
+      fx = fx_launch = true; fx_mul = static_cast<WT>(p.window->fx_mul); fx_limit = static_cast<WT>(p.window->fx_limit); fx_unmul = p.window->fx_unmul;
+      fx_carry = 4294967296.0 * fx_unmul;   // fx32: what one wrap of the u32 limb is worth
     }
   }
   // fixed-point layout: [wtot low limbs][32 trash slots][wtot high limbs][32 trash slots]; a lane with nothing
@@ -259,6 +272,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   auto shared_add1 = [&](int wbin, WT w, OT* out_row) {
     if constexpr (W == 0) {
       reds_add_u32(sh_lo + 4u * static_cast<unsigned>(wbin), 1u);
+    } else if constexpr (W == 3) {
+      // fx32: v = w * 2^s as ONE u32 limb.  The returned old value tells when the limb wraps; a wrap is worth
+      // 2^32 * 2^-s and goes straight to the float64 output (about one add in 512 for weights in [0, 1)).
+      const float vs = w * fx_mul;
+      const unsigned v = __float2uint_rn(vs);
+      if ((static_cast<float>(v) == vs) & (vs < fx_limit)) {
+        const unsigned old = atoms_add_u32(sh_lo + 4u * static_cast<unsigned>(wbin), v);
+        if (old + v < old) atomicAdd(out_row + window_to_global(wbin), fx_carry);
+      } else {
+        atomicAdd(out_row + window_to_global(wbin), static_cast<double>(w));
+      }
     } else {
       if (fx) {
         const WT vs = w * fx_mul;
@@ -269,6 +293,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
           const unsigned old = atoms_add_u32(sh_lo + 4u * static_cast<unsigned>(wbin), lo);
           hi += (old + lo < old) ? 1u : 0u;
           if (hi) reds_add_u32(sh_hi + 4u * static_cast<unsigned>(wbin), hi);
+        } else if (owned) {
+          s_redo = 1;      // no global add may precede the plain stores of an owned row
         } else {
           atomicAdd(out_row + window_to_global(wbin), static_cast<double>(w));
         }
@@ -290,6 +316,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
     if (len > s1 - s) len = s1 - s;
     if (len > kSegCap) len = kSegCap;
     OT* out_row = out + r * p.B;
+    owned = p.hist_mode == XHK_FULL && p.store_owned_rows && c0 == 0 && len == p.N;
 
     const T* px[KMAX];
     bool vec_ok = (KT != 0);
@@ -486,7 +513,36 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             }
           }
         }
-        if (W != 0 && fx) {
+        if constexpr (W == 3) {
+          // fx32 shared adds, straight-line: 4 ATOMS back to back; wraps of the limb and weights that are not exact
+          // at the scale (negative, too large, finer than 2^-s, NaN/inf) are rare and leave through global REDs
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            unsigned idx[4], lo[4], old[4], rare = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float vs = wv[u][e] * fx_mul;
+              const unsigned v = __float2uint_rn(vs);
+              const bool exact = (static_cast<float>(v) == vs) & (vs < fx_limit);
+              const bool valid = wb[u][e] >= 0;
+              const bool ok = valid & exact;
+              rare |= (valid & !exact) ? (1u << e) : 0u;
+              idx[e] = ok ? static_cast<unsigned>(wb[u][e]) : trash;
+              lo[e] = ok ? v : 0u;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) old[e] = atoms_add_u32(sh_lo + 4u * idx[e], lo[e]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) rare |= (old[e] + lo[e] < old[e]) ? (16u << e) : 0u;
+            if (rare) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (rare & (1u << e)) global_add(out_row, window_to_global(wb[u][e]), static_cast<double>(wv[u][e]));
+                if (rare & (16u << e)) global_add(out_row, window_to_global(wb[u][e]), fx_carry);
+              }
+            }
+          }
+        } else if (W != 0 && fx) {
           // fixed-point shared adds, straight-line: 4 low-limb ATOMS back to back, then the 4 high-limb REDs
           // (each takes the carry from the value its ATOMS returned)
           unsigned inexact = 0;
@@ -510,7 +566,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 #pragma unroll
             for (int e = 0; e < 4; ++e) reds_add_u32(sh_hi + 4u * idx[e], hi[e] + ((old[e] + lo[e] < old[e]) ? 1u : 0u));
           }
-          if (inexact) {   // rare: weights that are not exact multiples of the scale -> float64 global RED
+          if (inexact && owned) s_redo = 1;
+          else if (inexact) {   // rare: weights that are not exact multiples of the scale -> float64 global RED
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -523,18 +580,30 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
         }
       }
     }
-    s += len;
-
     // ---- flush the shared histogram of this row segment and clear it
     __syncthreads();
+    if constexpr (W == 1 || W == 2) {
+      // An owned row is written with plain stores, so nothing may reach it through global adds first.  If a weight
+      // of this segment did not fit the fixed-point form, drop the partial sums and redo the segment with float64
+      // shared adds (same shared-memory footprint).
+      if (s_redo) {     // uniform: written before the barrier above
+        __syncthreads();
+        for (int i = tid; i < wtot + 32; i += nthr) shist[i] = HT(0);
+        if (tid == 0) s_redo = 0;
+        fx = false;
+        __syncthreads();
+        continue;       // s has not advanced
+      }
+    }
+    s += len;
     if (p.hist_mode != XHK_GLOBAL) {
       const bool full = p.hist_mode == XHK_FULL;
-      const bool owned = full && p.store_owned_rows && c0 == 0 && len == p.N;
       unsigned int* lo32 = reinterpret_cast<unsigned int*>(shist);
       unsigned int* hi32 = lo32 + wcap;
       for (int b = tid; b < wtot; b += nthr) {
         OT v; bool nz;
         if constexpr (W == 0) { v = static_cast<OT>(shist[b]); nz = v != 0; shist[b] = 0u; }
+        else if constexpr (W == 3) { const unsigned q = lo32[b]; nz = q != 0u; v = static_cast<double>(q) * fx_unmul; lo32[b] = 0u; }
         else if (fx) {
           const long long iv = static_cast<long long>((static_cast<unsigned long long>(hi32[b]) << 32) | lo32[b]);
           nz = iv != 0; v = static_cast<double>(iv) * fx_unmul;
@@ -544,6 +613,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
         else if (nz) atomicAdd(out_row + (full ? static_cast<long long>(b) : window_to_global(b)), v);
       }
     }
+    fx = fx_launch;     // (a redone segment ran with float64 adds)
     __syncthreads();
   }
 }
@@ -555,13 +625,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 template <typename T, int KT>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant__ XhkParams p, XhkWindow* wout, int budget,
-                                                           int n_probe) {
+                                                           int budget32, int n_probe) {
   constexpr int KMAX = KT ? KT : XHK_MAX_VARS;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_moff[XHK_MAX_VARS + 1];
   __shared__ unsigned long long s_wmax;
-  __shared__ int s_fail, s_seen;
-  __shared__ double s_mul, s_limit;
+  __shared__ int s_fail, s_seen, s_fail32, s_budget;
+  __shared__ double s_mul, s_limit, s_mul32;
   const int K = KT ? KT : p.n_vars, tid = threadIdx.x, nthr = blockDim.x;
   T* sedges = reinterpret_cast<T*>(smem);
   const size_t edges_al = (static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15);
@@ -569,7 +639,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant
   unsigned int* marg = reinterpret_cast<unsigned int*>(smem + edges_al + ((static_cast<size_t>(p.n_lut_total) * 2 + 15) & ~static_cast<size_t>(15)));
   for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
   for (int i = tid; i < p.n_lut_total; i += nthr) slut[i] = p.lut[i];
-  if (tid == 0) { int o = 0; for (int k = 0; k < K; ++k) { s_moff[k] = o; o += p.nb[k]; } s_moff[K] = o; s_wmax = 0ull; s_fail = 0; s_seen = 0; }
+  if (tid == 0) { int o = 0; for (int k = 0; k < K; ++k) { s_moff[k] = o; o += p.nb[k]; } s_moff[K] = o; s_wmax = 0ull; s_fail = 0; s_seen = 0; s_fail32 = 0; s_budget = budget; }
   __syncthreads();
   const int mtot = s_moff[K];
   for (int i = tid; i < mtot; i += nthr) marg[i] = 0u;
@@ -638,25 +708,42 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_window(const __grid_constant
       const int sh = p.fx_vbits - 3 - e;          // v = w * 2^sh ; the largest probe weight maps below 2^(vbits-2)
       s_mul = ldexp(1.0, sh); s_limit = ldexp(1.0, p.fx_vbits);
       s_seen = (p.w_dtype == 1 && (sh > 100 || sh < -100)) ? -(1 << 30) : 0;   // outside fp32's exact power-of-two range
+      // fx32 candidate: the largest probe weight maps below 2^24 (one u32 limb per bin; k_hist<W = 3>)
+      const int sh32 = 23 - e;
+      s_mul32 = (budget32 > 0 && p.w_dtype == 1 && m > 0.0 && sh32 <= 100 && sh32 >= -100) ? ldexp(1.0, sh32) : 0.0;
     }
     __syncthreads();
-    int fails = 0;
+    int fails = 0, fails32 = 0;
 #pragma unroll
     for (int i = 0; i < PB; ++i) {
       if (i < nkeep) {
         const double vs = wkeep[i] * s_mul;
         if (!((static_cast<double>(__double2ll_rn(vs)) == vs) & (fabs(vs) < s_limit))) ++fails;
+        const double v32 = wkeep[i] * s_mul32;      // non-negative integer below 2^25 (NaN compares false)
+        if (!((v32 >= 0.0) & (v32 < 33554432.0) & (static_cast<double>(__double2ll_rn(v32)) == v32))) ++fails32;
       }
     }
     int seen = nkeep;
-    for (int o = 16; o > 0; o >>= 1) { fails += __shfl_xor_sync(0xffffffffu, fails, o); seen += __shfl_xor_sync(0xffffffffu, seen, o); }
-    if ((tid & 31) == 0 && seen) { atomicAdd(&s_fail, fails); atomicAdd(&s_seen, seen); }
+    for (int o = 16; o > 0; o >>= 1) {
+      fails += __shfl_xor_sync(0xffffffffu, fails, o); fails32 += __shfl_xor_sync(0xffffffffu, fails32, o);
+      seen += __shfl_xor_sync(0xffffffffu, seen, o);
+    }
+    if ((tid & 31) == 0 && seen) { atomicAdd(&s_fail, fails); atomicAdd(&s_fail32, fails32); atomicAdd(&s_seen, seen); }
     __syncthreads();
     if (tid == 0) {
-      wout->fx_mul = s_mul; wout->fx_unmul = 1.0 / s_mul; wout->fx_limit = s_limit;
-      wout->fx_ok = (s_seen > 0 && static_cast<long long>(s_fail) * 64 <= s_seen) ? 1 : 0;
+      if (s_mul32 > 0.0 && s_seen > 0 && static_cast<long long>(s_fail32) * 64 <= s_seen) {
+        wout->fx_mul = s_mul32; wout->fx_unmul = 1.0 / s_mul32; wout->fx_limit = 33554432.0;
+        wout->fx_ok = 1; wout->fx_mode = 32;
+        s_budget = budget32;                 // 4-byte bins: the window may hold twice as many
+      } else {
+        wout->fx_mul = s_mul; wout->fx_unmul = 1.0 / s_mul; wout->fx_limit = s_limit;
+        wout->fx_ok = (s_seen > 0 && static_cast<long long>(s_fail) * 64 <= s_seen) ? 1 : 0;
+        wout->fx_mode = wout->fx_ok ? 64 : 0;
+      }
     }
-  } else if (tid == 0) { wout->fx_ok = 0; wout->fx_mul = 0.0; wout->fx_unmul = 0.0; wout->fx_limit = 0.0; }
+  } else if (tid == 0) { wout->fx_ok = 0; wout->fx_mode = 0; wout->fx_mul = 0.0; wout->fx_unmul = 0.0; wout->fx_limit = 0.0; }
+  __syncthreads();
+  budget = s_budget;
 
   // ---- window: warp 0 bisects a density threshold (density of slice s of variable k = marg * nb_k, equal for
   //      all slices of a uniform distribution); the box of variable k spans the slices at or above the
@@ -827,6 +914,13 @@ XhkHistKernel pick_m(int K, int mode) {
 }
 
 
+// fx32 sibling (W = 3): floating-point data only (the host never asks for it with int64 data)
+template <typename T>
+XhkHistKernel pick_fx32(int K, int mode) {
+  if constexpr (std::is_floating_point<T>::value) return pick_m<T, 3>(K, mode);
+  else return nullptr;
+}
+
 template <typename T>
 XhkWindowKernel pick_window_t(int K) {
   switch (K) {
@@ -857,6 +951,7 @@ XhkColsKernel pick_cols_w(int w, int K) { return w == 0 ? pick_cols_k<T, 0>(K) :
 #define XHK_DEFINE_PICKERS(DT, T, ALLOW_FAST)                                                          \
   XhkHistKernel xhk_pick_hist_##DT(int w, int K, int mode) {                                           \
     if (!(ALLOW_FAST)) mode = 0;                                                                        \
+    if (w == 3) return pick_fx32<T>(K, mode);                                                           \
     return w == 0 ? pick_m<T, 0>(K, mode) : w == 1 ? pick_m<T, 1>(K, mode) : pick_m<T, 2>(K, mode);     \
   }                                                                                                     \
   XhkWindowKernel xhk_pick_window_##DT(int K) { return pick_window_t<T>(K); }                           \

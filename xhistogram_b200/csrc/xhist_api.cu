@@ -209,7 +209,7 @@ int prep_var(const double* e, int E, int k, bool force_search, XhkParams& p, std
   T* c = CSel<T>::row(p, k);
   c[XHK_C_LO] = lo; c[XHK_C_HI] = hi;
   p.uniform[k] = 0;
-  c[XHK_C_E0] = T(0); c[XHK_C_INV] = T(0); c[XHK_C_DELTA] = T(2); c[XHK_C_OMD] = T(-1);
+  c[XHK_C_E0] = T(0); c[XHK_C_INV] = T(0); c[XHK_C_DELTA] = T(2); c[XHK_C_OMD] = T(-1); c[XHK_C_CHALF] = T(-1);
   if (force_search) return XH_OK;
   // uniform fast path: usable when the edges are an arithmetic progression up to a small, bounded deviation
   const long double e0 = e[0], eN = e[E - 1];
@@ -234,7 +234,11 @@ int prep_var(const double* e, int E, int k, bool force_search, XhkParams& p, std
   // round delta up and 1-delta down in T
   T dT = static_cast<T>(static_cast<double>(delta)); if (static_cast<long double>(dT) < delta) dT = std::nextafter(dT, T(1));
   T oT = static_cast<T>(static_cast<double>(1.0L - delta)); if (static_cast<long double>(oT) > 1.0L - delta) oT = std::nextafter(oT, T(0));
-  c[XHK_C_E0] = e0T; c[XHK_C_INV] = invT; c[XHK_C_DELTA] = dT; c[XHK_C_OMD] = oT;
+  // one-compare form |frac - 0.5| <= chalf: frac - 0.5 is computed as t - (floor(t) + 0.5), which can round by up to
+  // half an ulp of 0.5 when t < 0.25, so chalf gives up 8u on top of delta (rounded down): never certain by mistake
+  T hT = static_cast<T>(static_cast<double>(0.5L - delta - 8 * u));
+  if (static_cast<long double>(hT) > 0.5L - delta - 8 * u) hT = std::nextafter(hT, T(0));
+  c[XHK_C_E0] = e0T; c[XHK_C_INV] = invT; c[XHK_C_DELTA] = dT; c[XHK_C_OMD] = oT; c[XHK_C_CHALF] = hT;
   p.uniform[k] = 1;
   return XH_OK;
 }
@@ -290,7 +294,8 @@ int prep_call(const xh_desc* d, Prep& pr) {
   }
   p.B = B;
   p.all_uniform = (B < 2147483646ll) ? 1 : 0;     // the fast kernel encodes global bins in an int
-  for (int k = 0; k < K; ++k) p.all_uniform = p.all_uniform && p.uniform[k];
+  // (and takes floor(t) from the mantissa of t + 1.5 * 2^23, which needs bin numbers below 2^21)
+  for (int k = 0; k < K; ++k) p.all_uniform = p.all_uniform && p.uniform[k] && p.nb[k] <= (1 << 21);
   long long mul = 1;
   for (int k = K - 1; k >= 0; --k) { p.gmul[k] = mul; mul *= p.nb[k]; }
   p.n_edges_total = static_cast<int>(d->dtype == XH_F32 ? tf.size() : d->dtype == XH_F64 ? td.size() : ti.size());

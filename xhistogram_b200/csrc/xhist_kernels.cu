@@ -107,7 +107,7 @@ XhkColsKernel pick_cols(int dtype, int w, int K) {
 // budget and measured slower than the general kernel (config 5: 4.18 vs 3.93 ms), so it is used for small records only.
 int kernel_mode(const XhkParams& p, int dtype) {
   if (dtype == 3) return 0;
-  if (p.all_uniform) return 1;
+  if (p.all_uniform) return p.tile_rows > 1 ? 3 : 1;   // row tiling is a compile-time variant of the fast kernel
   const int rec = p.n_vars * (dtype == 1 ? 4 : 8);
   return (p.all_branch_free && rec <= 16) ? 2 : 0;
 }
@@ -120,7 +120,7 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
   for (int dt = 1; dt <= 3; ++dt)
     for (int w = 0; w <= (dt == 3 ? 2 : 3); ++w)
       for (int k = 1; k <= 5; ++k)
-        for (int f = 0; f <= 2; ++f) {
+        for (int f = 0; f <= 3; ++f) {
           cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick(dt, w, k, f)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
           if (e != cudaSuccess) return e;
         }

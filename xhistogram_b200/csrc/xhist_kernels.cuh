@@ -11,7 +11,7 @@
 #endif
 // static shared memory of k_hist (window geometry + flags), rounded up; the host subtracts it from the dynamic budget
 #define XHK_STATIC_SMEM 80
-enum { XHK_C_LO = 0, XHK_C_HI = 1, XHK_C_E0 = 2, XHK_C_INV = 3, XHK_C_DELTA = 4, XHK_C_OMD = 5 };
+enum { XHK_C_LO = 0, XHK_C_HI = 1, XHK_C_E0 = 2, XHK_C_INV = 3, XHK_C_DELTA = 4, XHK_C_OMD = 5, XHK_C_CHALF = 6, XHK_C_SLOTS = 8 };
 
 // How the per-CTA shared-memory histogram is used.
 enum XhkHistMode {
@@ -51,8 +51,9 @@ struct XhkParams {
   //   [XHK_C_LO] smallest in-range value (effective first edge)   [XHK_C_HI] largest in-range value
   //   [XHK_C_E0],[XHK_C_INV] uniform path t = (x - e0) * inv
   //   [XHK_C_DELTA],[XHK_C_OMD] uniform path: bin certain iff delta <= frac(t) <= omd
-  float cf[XHK_MAX_VARS][6];
-  double cd[XHK_MAX_VARS][6];
+  //   [XHK_C_CHALF] the same test in one compare: certain iff |frac(t) - 0.5| <= chalf  (chalf <= 0.5 - delta)
+  float cf[XHK_MAX_VARS][XHK_C_SLOTS];
+  double cd[XHK_MAX_VARS][XHK_C_SLOTS];
   long long ci[XHK_MAX_VARS][2];    // int64 kernels: [XHK_C_LO], [XHK_C_HI] only (no uniform path)
   int nb[XHK_MAX_VARS];             // bins of variable k  (= n_edges - 1)
   int uniform[XHK_MAX_VARS];        // 1: uniform fast path usable for variable k

@@ -72,6 +72,32 @@ __device__ __forceinline__ bool uniform_guess(const XhkParams& p, int k, T x, in
   return (f >= Consts<T>::get(p, k, XHK_C_DELTA)) & (f <= Consts<T>::get(p, k, XHK_C_OMD));
 }
 
+// floor(t) as a T and as an int, for the branch-free fast path.  fp32: the integer part sits in the mantissa of
+// t + 1.5 * 2^23 rounded DOWN (valid for |t| < 2^22; beyond that — also NaN / inf — the integer lands outside
+// [0, 2^22) and the window test of the caller rejects it), so no F2I / I2F conversion is needed.
+template <typename T> struct FloorSplit;
+// run() returns floor(t) + kBias as the int (the caller folds kBias into its window offset).
+template <> struct FloorSplit<float> {
+  static constexpr int kBias = 0x4B400000;
+  static __device__ __forceinline__ void run(float t, float& jf, int& jraw) {
+    const float s = __fadd_rd(t, 12582912.0f);
+    jf = s - 12582912.0f;
+    jraw = __float_as_int(s);
+  }
+};
+template <> struct FloorSplit<double> {
+  static constexpr int kBias = 0;
+  static __device__ __forceinline__ void run(double t, double& jf, int& jraw) { jraw = __double2int_rd(t); jf = static_cast<double>(jraw); }
+};
+template <> struct FloorSplit<long long> {   // never used (no uniform path for int64)
+  static constexpr int kBias = 0;
+  static __device__ __forceinline__ void run(long long t, long long& jf, int& jraw) { jraw = static_cast<int>(t); jf = t; }
+};
+// keep a loop-invariant value in its register (under the 64-register cap ptxas otherwise rematerialises whole address
+// chains inside the hot loop)
+__device__ __forceinline__ unsigned pin(unsigned v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); return v; }
+
 // exact bin of any sample (slow but general): range test, uniform guess when usable, else search
 template <typename T> __device__ __forceinline__ T lut_inv(const XhkParams& p, int k);
 template <> __device__ __forceinline__ float lut_inv<float>(const XhkParams& p, int k) { return p.lut_invf[k]; }
@@ -149,7 +175,7 @@ template <> struct WType<2> { using type = double; };
 // ---------------------------------------------------------------------------------------------
 template <typename T, int W, int KT, int MODE>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__ XhkParams p) {
-  constexpr bool FAST = (MODE == 1);
+  constexpr bool FAST = (MODE == 1 || MODE == 3);   // 3: the same with row tiling compiled in (1: compiled out)
   using HT = typename std::conditional<W == 0 || W == 3, unsigned int, double>::type;   // shared accumulator
   using OT = typename std::conditional<W == 0, unsigned long long, double>::type;       // global accumulator
   using WT = typename WType<W>::type;
@@ -170,7 +196,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   T* sedges = reinterpret_cast<T*>(smem);
   const size_t edges_al = (static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15);
   unsigned short* slut = reinterpret_cast<unsigned short*>(smem + edges_al);
-  HT* shist = reinterpret_cast<HT*>(smem + edges_al + ((static_cast<size_t>(p.n_lut_total) * 2 + 15) & ~static_cast<size_t>(15)));
+  // histogram region: [32 trash slots (u32)][bins ...]; `shist` points at the bins.  A lane with nothing to add puts a
+  // zero into its own trash slot (index lane - 32 relative to the bins), which keeps the shared adds free of branches.
+  unsigned int* const hregion = reinterpret_cast<unsigned int*>(smem + edges_al + ((static_cast<size_t>(p.n_lut_total) * 2 + 15) & ~static_cast<size_t>(15)));
+  HT* const shist = reinterpret_cast<HT*>(hregion + 32);
 
   for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
   for (int i = tid; i < p.n_lut_total; i += nthr) slut[i] = p.lut[i];
@@ -192,9 +221,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   }
   // row tiling: the shared histogram holds tile_rows rows; a sample's bin is offset by (local row) * (bins per row),
   // obtained for free by seeding the Horner evaluation of the joint bin with the local row
-  const bool tiled = p.tile_rows > 1;
+  const bool tiled = (MODE == 3) || (MODE != 1 && p.tile_rows > 1);
   wtot *= p.tile_rows;
-  for (int i = tid; i < (W == 0 ? wtot : wtot + 32); i += nthr) shist[i] = HT(0);   // (+ the trash slots)
+  const int hwords = (wtot + 32) * static_cast<int>(sizeof(HT) / 4);               // (+ the trash slots)
+  for (int i = tid; i < hwords; i += nthr) hregion[i] = 0u;
   // weighted accumulation mode (uniform for the launch): exact fixed point in two u32 limbs, or float64 adds
   // `fx` can fall back to float64 adds for one row segment (see s_redo), hence not const
   bool fx = false, fx_launch = false; WT fx_mul = WT(0), fx_limit = WT(0); double fx_unmul = 0.0, fx_carry = 0.0;
@@ -205,12 +235,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       fx_carry = 4294967296.0 * fx_unmul;   // fx32: what one wrap of the u32 limb is worth
     }
   }
-  // fixed-point layout: [wtot low limbs][32 trash slots][wtot high limbs][32 trash slots]; a lane with nothing
-  // to add puts a zero into its own trash slot, which keeps the weighted shared adds free of branches
+  // two-limb fixed point: [32 trash][wtot low limbs][32 trash][wtot high limbs]
   const int wcap = wtot + 32;
-  const unsigned sh_lo = static_cast<unsigned>(__cvta_generic_to_shared(shist));   // counts / lo limbs / doubles
+  const unsigned sh_lo = pin(static_cast<unsigned>(__cvta_generic_to_shared(shist)));   // counts / lo limbs / doubles
   const unsigned sh_hi = sh_lo + 4u * static_cast<unsigned>(wcap);                  // hi limbs (fixed point)
-  const unsigned trash = static_cast<unsigned>(wtot + (tid & 31));
+  const unsigned trash = pin(static_cast<unsigned>((tid & 31) - 32));   // negative index: the lane's trash slot
   __syncthreads();
 
   OT* const out = static_cast<OT*>(p.out);
@@ -356,6 +385,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
     if constexpr (KT != 0) {
       // vector body: 4 samples per 16-byte load, U loads in flight per array and thread
       constexpr int U = (sizeof(T) * KMAX + (W == 0 ? 0 : sizeof(WT)) <= 12) ? 2 : 1;
+      const float fx_mulp = pin(static_cast<float>(fx_mul) * 2.98023223876953125e-8f);   // fx32: fx_mul * 2^-25
+      int jbias[KMAX];          // fused fast path: window offset of floor(t) + FloorSplit::kBias
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) jbias[k] = wlo[k] + FloorSplit<T>::kBias;
       for (long long g = tid; g < nvec; g += static_cast<long long>(U) * nthr) {
         T xv[U][KMAX][4];
         WT wv[U][4];
@@ -450,6 +483,104 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
                                             local_row(head + 4 * (g + static_cast<long long>(idx >> 2) * nthr) + (idx & 3)));
             if (wbin >= 0) shared_add1(wbin, wsel, out_row);
           }
+        } else if constexpr (FAST && (W == 0 || W == 3)) {
+          // ---- fused classify + accumulate (counts and one-limb weights).  Built to stay off the half-rate ALU
+          // pipe, which bounds this kernel: floor(t) from the mantissa trick (FADDs), certainty as ONE compare
+          // |t - (floor(t) + 0.5)| <= chalf, `live` as the seed of the predicate chain, no per-sample masks.  A sample
+          // that is not (certain and inside the window) adds nothing here (zero into a trash slot) and is picked up
+          // by the side loop below; idx == trash is how it is recognised there.
+          unsigned idx[U][4];
+          unsigned worst = 0;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool live = (u == 0) || (g + static_cast<long long>(u) * nthr < nvec);
+            unsigned vv[4], old[4];
+            bool any_rare = false;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              bool good = live; int wbin = local_row(head + 4 * (g + static_cast<long long>(u) * nthr) + e);
+#pragma unroll
+              for (int k = 0; k < KMAX; ++k) {
+                const T t = (xv[u][k][e] - Consts<T>::get(p, k, XHK_C_E0)) * Consts<T>::get(p, k, XHK_C_INV);
+                T jf; int jraw;
+                FloorSplit<T>::run(t, jf, jraw);
+                const T d = t - (jf + T(0.5));
+                const unsigned jw = static_cast<unsigned>(jraw - jbias[k]);
+                good = good & (fabs(d) <= Consts<T>::get(p, k, XHK_C_CHALF)) & (jw < static_cast<unsigned>(wlen[k]));
+                wbin = wbin * wlen[k] + static_cast<int>(jw);
+              }
+              idx[u][e] = good ? static_cast<unsigned>(wbin) : trash;
+              if constexpr (W == 3) {
+                // v = round(clamp(w * 2^s, 0, 2^25)); the clamp rides on the multiplier (FMUL.SAT).  A sample that
+                // is not `good` adds its v to the trash slot (never read; checks below skip it)
+                const float we = wv[u][e];
+                vv[e] = __float2uint_rn(__saturatef(we * fx_mulp) * 33554432.0f);
+                any_rare = any_rare | (static_cast<float>(vv[e]) != we * static_cast<float>(fx_mul));
+              }
+            }
+            if constexpr (W == 0) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) reds_add_u32(sh_lo + 4u * idx[u][e], 1u);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) old[e] = atoms_add_u32(sh_lo + 4u * idx[u][e], vv[e]);
+              // v < 2^26: the limb wrapped iff its top bit went from 1 to 0
+              unsigned wrapped = 0;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) wrapped |= old[e] & ~(old[e] + vv[e]);
+              if (any_rare | (static_cast<int>(wrapped) < 0)) {
+                // rare: the limb wrapped (worth 2^32 * 2^-s), or v is not the weight (negative, too large, finer
+                // than the scale, NaN / inf): the float64 output gets the difference, which is exact in float64
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (static_cast<int>(idx[u][e]) >= 0) {
+                    const double diff = static_cast<double>(wv[u][e]) - static_cast<double>(vv[e]) * fx_unmul;
+                    if (diff != 0.0) global_add(out_row, window_to_global(static_cast<int>(idx[u][e])), diff);
+                    if (old[e] + vv[e] < old[e]) global_add(out_row, window_to_global(static_cast<int>(idx[u][e])), fx_carry);
+                  }
+                }
+              }
+            }
+            worst = max(worst, max(max(idx[u][0], idx[u][1]), max(idx[u][2], idx[u][3])));
+          }
+          if (worst >= 0x80000000u) {
+            // side loop, one sample per trip (a lane rarely has more than one): certain and in range but outside
+            // the window -> global RED; everything else (uncertain, out of range, NaN) -> exact path
+            unsigned side = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                side |= (static_cast<int>(idx[u][e]) < 0 && g + static_cast<long long>(u) * nthr < nvec) ? (1u << (4 * u + e)) : 0u;
+            while (side) {
+              const int sidx = __ffs(side) - 1;
+              side &= side - 1;
+              T x[KMAX]; WT wsel = WT(1);
+#pragma unroll
+              for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (sidx == 4 * u + e) {
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
+                    wsel = wv[u][e];
+                  }
+              bool sure = true; long long gbin = 0;
+#pragma unroll
+              for (int k = 0; k < KMAX; ++k) {
+                int jx; const bool certain = uniform_guess<T>(p, k, x[k], jx);
+                sure = sure & certain & (static_cast<unsigned>(jx) < static_cast<unsigned>(p.nb[k]));
+                gbin = gbin * p.nb[k] + jx;
+              }
+              if (sure && !tiled && p.hist_mode != XHK_FULL) global_add(out_row, gbin, static_cast<double>(wsel));
+              else {
+                const int wbin = general_sample(x, static_cast<double>(wsel), out_row,
+                                                local_row(head + 4 * (g + static_cast<long long>(sidx >> 2) * nthr) + (sidx & 3)));
+                if (wbin >= 0) shared_add1(wbin, wsel, out_row);
+              }
+            }
+          }
+          continue;   // (the generic accumulation below serves the other forms)
         } else if constexpr (FAST) {
           // phase A (branch-free, U*4*K independent chains): guess, certainty, window test
           unsigned side = 0;   // bit (4u+e) set: that sample needs the side path
@@ -588,7 +719,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       // shared adds (same shared-memory footprint).
       if (s_redo) {     // uniform: written before the barrier above
         __syncthreads();
-        for (int i = tid; i < wtot + 32; i += nthr) shist[i] = HT(0);
+        for (int i = tid; i < hwords; i += nthr) hregion[i] = 0u;
         if (tid == 0) s_redo = 0;
         fx = false;
         __syncthreads();
@@ -909,6 +1040,7 @@ XhkHistKernel pick_m(int K, int mode) {
   if constexpr (std::is_floating_point<T>::value) {   // int64 data: general kernel only
     if (mode == 1) return pick_k<T, W, 1>(K);
     if (mode == 2) return pick_k<T, W, 2>(K);
+    if (mode == 3) return pick_k<T, W, 3>(K);
   }
   return pick_k<T, W, 0>(K);
 }

@@ -241,11 +241,7 @@ def main():
     def step_device():
         """The user call with inputs resident in HBM: histogram (+ all-reduce of the partials) + density."""
         if comm is None:
-            # core.histogram with device arrays; kernel time of the call is read back for the roofline
-            h = core._bincount(x, y, w, weights=True, axis=None, bins=bins, _timing=timing).squeeze()
-            kernel_ms.append(timing["kernel_ms"])
-            areas = np.outer(np.diff(EDGES), np.diff(EDGES))
-            return h / areas / h.sum()
+            return core.histogram(x, y, bins=bins, weights=w, density=True)[0]     # density finished on the device
         h, _ = D.histogram(x, y, bins=bins, weights=w, density=True, comm=comm, sharded_axis=0)
         return h
 
@@ -304,10 +300,10 @@ def main():
     value = world * n / (ms_per_step * 1e-3)
 
     # per-launch kernel time for the roofline (single-GPU path reads it from the library's own events)
-    if not kernel_ms:
-        for _ in range(3):
-            core._bincount(x, y, w, weights=True, axis=None, bins=bins, _timing=timing)
-            kernel_ms.append(timing["kernel_ms"])
+    # (the library's own CUDA events around the kernels of one call, on its stream; same launches as a step)
+    for _ in range(10):
+        core._bincount(x, y, w, weights=True, axis=None, bins=bins, _timing=timing, _density_widths=[np.diff(EDGES)] * 2)
+        kernel_ms.append(timing["kernel_ms"])
     k_ms = float(np.mean(kernel_ms))
 
     # ---- end-to-end: pinned host inputs, H2D inside the timed region, result read back
@@ -379,7 +375,7 @@ def main():
                    "accumulate": "float64 (np.bincount semantics), fp32 compare on round-up edges"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * n * 12, "d2h_bytes_per_step": world * NBINS * NBINS * 8,
                 "steps": e2e_steps, "matches_device_result": e2e_ok},
-        "gpu_launches": args.steps * 3 * world,   # probe + the two sibling k_hist launches (one of them returns at once)
+        "gpu_launches": args.steps * (4 if world == 1 else 3) * world,   # probe, the two sibling k_hist launches (one returns at once), density
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,

@@ -51,6 +51,8 @@ typedef enum xh_mem { XH_HOST = 0, XH_DEVICE = 1 } xh_mem;
 #define XH_FLAG_FORCE_SEARCH 4u /* testing: bypass the uniform-edge fast path, binary search only           */
 #define XH_FLAG_FORCE_WINDOW 8u /* testing: use the windowed shared-memory histogram even if all bins fit   */
 #define XH_FLAG_NO_FX32 16u     /* testing: fp32 weights never take the one-limb (4 bytes per bin) accumulation  */
+#define XH_FLAG_DENSITY 32u     /* finish the density on the device (core.py:444-462): out becomes float64
+                                   counts / bin areas / row sum, also without weights; needs widths[]         */
 
 /*
  * One histogram request over a logical (n_rows, n_cols) block: histogram along the
@@ -98,10 +100,14 @@ typedef struct xh_desc {
   float* kernel_ms;                   /* optional: device time of the kernels of this call   */
   const int64_t* iedges[XH_MAX_VARS]; /* dtype == XH_I64: the edges as int64 (edges[] unused)  */
   int64_t n_inner;                    /* > 1: column layout (reduced axes lead, see below); 0/1: row layout */
+  const double* widths[XH_MAX_VARS];  /* XH_FLAG_DENSITY: HOST np.diff(edges_k) as float64, n_edges[k]-1 values  */
+  int32_t widths_f32[XH_MAX_VARS];    /* 1: numpy holds these widths as float32 (a product of two such is
+                                         rounded to float32, as np.multiply.outer does in core.py:447-454)      */
 } xh_desc;
 
 /* library / device lifecycle --------------------------------------------------------- */
 int xh_version(void);                                   /* major*1000 + minor */
+int xh_desc_size(void);                                 /* sizeof(xh_desc): lets a binding check its mirror of the struct */
 int xh_device_count(int* count);
 int xh_init(int device);                                /* create the per-device context (idempotent) */
 int xh_shutdown(void);                                  /* release every context, workspace and communicator */

@@ -13,7 +13,7 @@ from xhistogram_b200 import core
 
 
 def _oracle_desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing,
-                      out_device=None, n_inner=0):
+                      out_device=None, n_inner=0, density_widths=None):
     def full(a, stride):
         a = np.asarray(a)
         if n_inner > 1:   # column layout: (outer, N, inner) C-contiguous -> logical rows a*inner + m
@@ -36,7 +36,13 @@ def _oracle_desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem,
         edges = [np.asarray(b, dtype=np.float64) for b in bins]
     ww = None if w is None else full(w, wstride)
     B = int(np.prod([len(b) - 1 for b in bins]))
-    return O.block_bincount(data, edges, ww).reshape(M, B)
+    h = O.block_bincount(data, edges, ww).reshape(M, B)
+    if density_widths is not None:     # what k_density does on the device (core.py:444-462)
+        import functools
+        areas = functools.reduce(np.multiply.outer, density_widths).reshape(1, B)
+        with np.errstate(all="ignore"):
+            h = h / areas / h.sum(axis=1, keepdims=True)
+    return h
 
 
 @pytest.fixture
@@ -99,9 +105,9 @@ def test_three_variable_density(patched):
 def test_weight_row_broadcast_is_passed_with_stride_zero(monkeypatch):
     seen = {}
 
-    def spy(arrs, strides, w, wstride, *rest):
+    def spy(arrs, strides, w, wstride, *rest, **kw):
         seen["wstride"], seen["wshape"] = wstride, w.shape
-        return _oracle_desc_call(arrs, strides, w, wstride, *rest)
+        return _oracle_desc_call(arrs, strides, w, wstride, *rest, **kw)
 
     monkeypatch.setattr(core, "_desc_call", spy)
     x = np.random.default_rng(4).standard_normal((5, 20))

@@ -103,6 +103,45 @@ def test_fx32_weights(k, dtype, layout):
         assert_hist_equal(h, want[0], rtol=1e-6)
 
 
+@pytest.mark.parametrize("case", ["1d_f32_edges", "2d_rows", "3d_mixed", "big_B", "short_rows", "empty_row"])
+def test_density_on_device(case):
+    """k_density reproduces core.py:444-462 (counts / bin areas / row sums, float32 products where numpy has them):
+    bit-exact for counts (integer row sums are exact), 1e-6 for weighted sums."""
+    import functools
+    r = np.random.default_rng(11)
+    if case == "1d_f32_edges":
+        args, kw = [r.random(100_000).astype(np.float32)], dict(bins=50)                       # int bins on fp32 -> fp32 edges
+    elif case == "2d_rows":
+        args = [r.standard_normal((9, 20_000)).astype(np.float32) for _ in range(2)]
+        kw = dict(bins=[np.linspace(-3, 3, 41).astype(np.float32), np.linspace(-3, 3, 31).astype(np.float32)], axis=1)
+    elif case == "3d_mixed":
+        args = [r.standard_normal(50_000) for _ in range(3)]
+        kw = dict(bins=[np.linspace(-3, 3, 11).astype(np.float32), np.linspace(-3, 3, 13).astype(np.float32),
+                        np.sort(r.uniform(-3, 3, 9))])
+    elif case == "big_B":
+        args = [r.standard_normal(400_000).astype(np.float32) for _ in range(2)]
+        kw = dict(bins=[np.linspace(-4, 4, 301), np.linspace(-4, 4, 201)])
+    elif case == "short_rows":
+        args, kw = [r.standard_normal((5000, 40))], dict(bins=np.linspace(-2, 2, 9), axis=-1)
+    else:
+        x = r.standard_normal((3, 1000)); x[1] = 50.0                                          # a row with nothing in range
+        args, kw = [x], dict(bins=np.linspace(-2, 2, 9), axis=-1)
+    for weighted in (False, True):
+        w = r.random(args[0].shape, dtype=np.float32) if weighted else None
+        with np.errstate(all="ignore"):
+            h, edges = core.histogram(*args, weights=w, density=True, **kw)
+            c, _ = core.histogram(*args, weights=w, **kw)                                       # same kernels, no density
+            areas = functools.reduce(np.multiply.outer, [np.diff(e) for e in edges])
+            K = len(args)
+            sums = c.sum(axis=tuple(range(-K, 0)))
+            want = c / areas / np.reshape(sums, sums.shape + (1,) * K)
+        assert h.dtype == np.float64
+        if weighted:
+            assert_hist_equal(h, want, rtol=1e-6)
+        else:
+            assert np.array_equal(h, want, equal_nan=True)
+
+
 def test_fx32_limb_wraps_are_exact():
     """Every sample in ONE bin with weights just below 1: the u32 limb wraps every ~256 adds; the sum stays exact."""
     n = 3_000_000

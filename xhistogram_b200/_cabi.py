@@ -19,6 +19,7 @@ XH_FLAG_FORCE_GLOBAL = 2
 XH_FLAG_FORCE_SEARCH = 4
 XH_FLAG_FORCE_WINDOW = 8
 XH_FLAG_NO_FX32 = 16
+XH_FLAG_DENSITY = 32
 XH_NCCL_UNIQUE_ID_BYTES = 128
 
 _ERRORS = {
@@ -56,6 +57,8 @@ class XhDesc(C.Structure):
         ("kernel_ms", C.POINTER(C.c_float)),
         ("iedges", C.POINTER(C.c_int64) * XH_MAX_VARS),
         ("n_inner", C.c_int64),
+        ("widths", C.POINTER(C.c_double) * XH_MAX_VARS),
+        ("widths_f32", C.c_int32 * XH_MAX_VARS),
     ]
 
 
@@ -66,6 +69,7 @@ _lock = threading.Lock()
 # name -> (restype, argtypes): every symbol include/xhist_b200.h declares
 PROTOTYPES = {
     "xh_version": (C.c_int, []),
+    "xh_desc_size": (C.c_int, []),
     "xh_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "xh_init": (C.c_int, [C.c_int]),
     "xh_shutdown": (C.c_int, []),
@@ -116,6 +120,9 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        if handle.xh_desc_size() != C.sizeof(XhDesc):
+            raise ImportError(f"{LIB_NAME} was built from a different include/xhist_b200.h (struct xh_desc is "
+                              f"{handle.xh_desc_size()} bytes there, {C.sizeof(XhDesc)} here): rebuild it")
         _lib = handle
         return _lib
 

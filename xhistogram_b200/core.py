@@ -254,7 +254,7 @@ def _rows_view(a, axis, full):
 
 
 def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, block_size=None,
-              _devices=None, _flags=0, _timing=None, _out_device=None):
+              _devices=None, _flags=0, _timing=None, _out_device=None, _density_widths=None):
     """GPU replacement of the reference's ``_bincount`` (core.py:197-247).
 
     Same contract: ``all_arrays`` are mutually broadcast arrays of identical shape (weights last
@@ -262,6 +262,9 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
     ``kept_axes_shape (with 1 for every reduced axis) + (nbins_1, ..., nbins_K)``, int64 without
     weights and float64 with.  It is what dask's ``blockwise`` maps over chunks, so it is
     re-entrant (the native library serialises per device).
+
+    ``_density_widths`` (list of ``np.diff(edges_k)``) makes the library finish the density on the device
+    (counts / bin areas / row sums, core.py:444-462) so that the float64 result is all that crosses PCIe.
     """
     all_arrays = list(all_arrays)
     a0 = all_arrays[0]
@@ -295,7 +298,7 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
             outer, N, n_inner = col
             M = outer * n_inner
         dev = views[0][3]
-        out = _device_call(views, wview, bins, M, N, dev, _flags, _timing, _out_device, n_inner)
+        out = _device_call(views, wview, bins, M, N, dev, _flags, _timing, _out_device, n_inner, _density_widths)
         if _out_device is not None:
             return out                                       # DeviceArray (M * prod(bins)), stays in HBM
         return out.reshape(kept_axes_shape + nbins)
@@ -318,13 +321,13 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
             outer, N, n_inner = col
             wdt = _xh_dtype(w.dtype) if w is not None else _cabi.XH_NONE
             out = _desc_call(data, [N] * len(data), w, N if w is not None else 0, bins, outer * n_inner, N, xdt_of(iplan, data), wdt,
-                             _cabi.XH_HOST, _default_device(), None, _flags, _timing, None, n_inner)
+                             _cabi.XH_HOST, _default_device(), None, _flags, _timing, None, n_inner, _density_widths)
             return out.reshape(kept_axes_shape + nbins)
     rows = [_rows_view(a, ax, full) for a in data]
     M, N = rows[0][2], rows[0][3]
     wrow = _rows_view(w, ax, full) if w is not None else None
     xdt = xdt_of(iplan, data)
-    out = _host_call([r[0] for r in rows], [r[1] for r in rows], wrow, bins, M, N, xdt, _devices, _flags, _timing)
+    out = _host_call([r[0] for r in rows], [r[1] for r in rows], wrow, bins, M, N, xdt, _devices, _flags, _timing, _density_widths)
     return out.reshape(kept_axes_shape + nbins)
 
 
@@ -332,23 +335,23 @@ def xdt_of(iplan, data):
     return _cabi.XH_I64 if iplan is not None else _xh_dtype(data[0].dtype)
 
 
-def _host_call(arrs, strides, wrow, bins, M, N, xdt, devices, flags, timing):
+def _host_call(arrs, strides, wrow, bins, M, N, xdt, devices, flags, timing, density_widths=None):
     d_dtype = xdt
     w2d, wstride, wdt = (wrow[0], wrow[1], _xh_dtype(wrow[0].dtype)) if wrow is not None else (None, 0, _cabi.XH_NONE)
     return _desc_call(arrs, strides, w2d, wstride, bins, M, N, d_dtype, wdt, _cabi.XH_HOST,
-                      devices[0] if devices else _default_device(), devices, flags, timing)
+                      devices[0] if devices else _default_device(), devices, flags, timing, density_widths=density_widths)
 
 
-def _device_call(views, wview, bins, M, N, dev, flags, timing, out_device=None, n_inner=0):
+def _device_call(views, wview, bins, M, N, dev, flags, timing, out_device=None, n_inner=0, density_widths=None):
     ptrs = [v[0] for v in views]
     wptr = wview[0] if wview else None
     wdt = _xh_dtype(wview[2]) if wview else _cabi.XH_NONE
     return _desc_call(ptrs, [N] * len(ptrs), wptr, N if wview else 0, bins, M, N, _xh_dtype(views[0][2]), wdt,
-                      _cabi.XH_DEVICE, dev, None, flags, timing, out_device, n_inner)
+                      _cabi.XH_DEVICE, dev, None, flags, timing, out_device, n_inner, density_widths)
 
 
 def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing, out_device=None,
-               n_inner=0):
+               n_inner=0, density_widths=None):
     K = len(arrs)
     if K > _cabi.XH_MAX_VARS:
         raise NotImplementedError(f"at most {_cabi.XH_MAX_VARS} variables are supported")
@@ -376,6 +379,14 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
         d.w_row_stride = wstride
         if mem == _cabi.XH_HOST and not w.size:
             d.w_dtype = _cabi.XH_NONE
+    if density_widths is not None:
+        # density on the device: widths as float64 values plus how numpy holds them (float32 products round to float32)
+        d.flags |= _cabi.XH_FLAG_DENSITY
+        for k in _range(K):
+            wd = np.ascontiguousarray(density_widths[k], dtype=np.float64)
+            d.widths[k] = wd.ctypes.data_as(C.POINTER(C.c_double))
+            d.widths_f32[k] = 1 if np.asarray(density_widths[k]).dtype == np.float32 else 0
+            keep.append(wd)
     B = int(np.prod([len(b) - 1 for b in bins], dtype=np.int64))
     if out_device is not None:
         if out_device.size != M * B or out_device.dtype.itemsize != 8:
@@ -383,9 +394,9 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
         out = out_device
         d.out, d.out_mem = out_device.ptr, _cabi.XH_DEVICE
     else:
-        out = np.empty((M, B), dtype=np.int64 if w is None else np.float64)
+        out = np.empty((M, B), dtype=np.int64 if (w is None and density_widths is None) else np.float64)
         if M * N == 0 or B == 0:
-            out[...] = 0
+            out[...] = np.nan if (density_widths is not None and B) else 0      # 0 / area / 0, as numpy computes it
             return out
         d.out = out.ctypes.data
     ms = C.c_float(0.0)
@@ -477,6 +488,9 @@ def histogram(*args, bins=None, range=None, axis=None, weights=None, density=Fal
 
     drop_axes = tuple(axis) if axis is not None else input_axes
     bincount_kwargs = dict(weights=has_weights, axis=axis, bins=bins, density=density, block_size=block_size)
+    # density finished on the device (single device, float edges): only the float64 result crosses PCIe
+    device_density = (density and not is_dask_array and (devices is None or len(devices) <= 1)
+                      and all(np.asarray(b).dtype in (np.float32, np.float64) and len(b) >= 2 for b in bins))
 
     if is_dask_array:
         import dask.array as dsa                                      # core.py:403-439, _bincount now on the GPU
@@ -492,9 +506,12 @@ def histogram(*args, bins=None, range=None, axis=None, weights=None, density=Fal
                                    adjust_chunks=adjust_chunks, meta=np.array((), dtype), **bincount_kwargs)
         bin_counts = bin_counts.sum(drop_axes)
     else:
-        bin_counts = _bincount(*all_arrays, _devices=devices, **bincount_kwargs).squeeze(drop_axes)
+        widths = [np.diff(b) for b in bins] if device_density else None
+        bin_counts = _bincount(*all_arrays, _devices=devices, _density_widths=widths, **bincount_kwargs).squeeze(drop_axes)
 
-    if density:                                                      # core.py:444-462
+    if device_density:
+        h = bin_counts                                               # core.py:444-462 done by k_density
+    elif density:                                                    # core.py:444-462
         bin_widths = [np.diff(b) for b in bins]
         bin_areas = functools.reduce(np.multiply.outer, bin_widths)  # K=1: widths, K=2: outer, K>=3: N-D outer
         bin_axes = tuple(_range(-n_inputs, 0))

@@ -100,6 +100,10 @@ struct Ctx {
   size_t bcast_cap = 0;
   void* flush = nullptr;             // L2 flush scratch
   size_t flush_bytes = 0;
+  double* widths = nullptr;          // device bin widths (density)
+  size_t widths_cap = 0;
+  void* rowsums = nullptr;           // device row sums (density), 8 bytes per row
+  size_t rowsums_cap = 0;
   void* outbuf = nullptr;            // device histogram when the caller's out is host memory
   size_t outbuf_cap = 0;
   void* comm = nullptr;              // NCCL communicator (multi-process mode)
@@ -480,6 +484,10 @@ int validate(const xh_desc* d) {
   if ((d->flags & XH_FLAG_NO_ZERO) && d->out_mem != XH_DEVICE) return fail(XH_ERR_INVALID, "XH_FLAG_NO_ZERO needs a device out");
   if (d->n_inner > 1 && (d->n_rows % d->n_inner) != 0) return fail(XH_ERR_INVALID, "column layout: n_rows must be a multiple of n_inner");
   if (d->n_inner < 0) return fail(XH_ERR_INVALID, "negative n_inner");
+  if (d->flags & XH_FLAG_DENSITY) {
+    if (d->flags & XH_FLAG_NO_ZERO) return fail(XH_ERR_INVALID, "XH_FLAG_DENSITY cannot be combined with XH_FLAG_NO_ZERO");
+    for (int k = 0; k < d->n_vars; ++k) if (!d->widths[k]) return fail(XH_ERR_INVALID, "XH_FLAG_DENSITY needs widths[%d]", k);
+  }
   return XH_OK;
 }
 
@@ -724,6 +732,31 @@ int hist_locked(Ctx* c, const xh_desc* d) {
       }
     }
   }
+  std::vector<double> wh;               // (stays alive until the stream is synchronised below)
+  if (rc == XH_OK && (d->flags & XH_FLAG_DENSITY) && out_bytes) {
+    // core.py:444-462 on the device, in place: counts / bin areas / row sums
+    int nb[XH_MAX_VARS], f32[XH_MAX_VARS];
+    for (int k = 0; k < d->n_vars; ++k) {
+      nb[k] = d->n_edges[k] - 1; f32[k] = d->widths_f32[k];
+      wh.insert(wh.end(), d->widths[k], d->widths[k] + nb[k]);
+    }
+    if (wh.size() > c->widths_cap) {
+      if (c->widths) cudaFree(c->widths);
+      c->widths = nullptr; c->widths_cap = 0;
+      const size_t cap = std::max<size_t>(wh.size(), 4096);
+      CU(cudaMalloc(&c->widths, cap * sizeof(double)));
+      c->widths_cap = cap;
+    }
+    if (B > 1024 && static_cast<size_t>(M) > c->rowsums_cap) {
+      if (c->rowsums) cudaFree(c->rowsums);
+      c->rowsums = nullptr; c->rowsums_cap = 0;
+      const size_t cap = std::max<size_t>(static_cast<size_t>(M), 4096);
+      CU(cudaMalloc(&c->rowsums, cap * 8));
+      c->rowsums_cap = cap;
+    }
+    CU(cudaMemcpyAsync(c->widths, wh.data(), wh.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(xhk_launch_density(dev_out, M, B, d->w_dtype == XH_NONE ? 1 : 0, c->widths, nb, f32, d->n_vars, c->rowsums, s));
+  }
   if (rc == XH_OK && d->kernel_ms) cudaEventRecord(c->ev1, s);
   if (rc == XH_OK && d->out_mem == XH_HOST && out_bytes) {
     cudaError_t e = cudaMemcpyAsync(d->out, dev_out, out_bytes, cudaMemcpyDeviceToHost, s);
@@ -742,6 +775,7 @@ int hist_locked(Ctx* c, const xh_desc* d) {
 extern "C" {
 
 int xh_version(void) { return XH_VERSION_MAJOR * 1000 + XH_VERSION_MINOR; }
+int xh_desc_size(void) { return static_cast<int>(sizeof(xh_desc)); }
 
 int xh_last_error(char* buf, size_t len) {
   if (!buf || !len) return XH_ERR_INVALID;
@@ -772,6 +806,8 @@ int xh_shutdown(void) {
     if (c->bcast) cudaFree(c->bcast);
     if (c->flush) cudaFree(c->flush);
     if (c->outbuf) cudaFree(c->outbuf);
+    if (c->widths) cudaFree(c->widths);
+    if (c->rowsums) cudaFree(c->rowsums);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->copied[i]); cudaEventDestroy(c->consumed[i]); }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->tev0); cudaEventDestroy(c->tev1);
     cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
@@ -808,6 +844,7 @@ int xh_hist_multi(const xh_desc* d, const int32_t* devices, int32_t n_dev) {
   if (!devices || n_dev < 1) return fail(XH_ERR_INVALID, "need at least one device");
   if (d->mem != XH_HOST || d->out_mem != XH_HOST) return fail(XH_ERR_INVALID, "xh_hist_multi takes host data and a host out");
   if (n_dev == 1) { xh_desc b = *d; b.device = devices[0]; return xh_hist(&b); }
+  if (d->flags & XH_FLAG_DENSITY) return fail(XH_ERR_UNSUPPORTED, "xh_hist_multi: the density is taken after the reduction, on the caller side");
   if (d->n_inner > 1) return fail(XH_ERR_UNSUPPORTED, "xh_hist_multi does not take the column layout; shard the kept axis on the caller side");
   const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
   const size_t tsz = dsize(d->dtype), wsz = dsize(d->w_dtype);

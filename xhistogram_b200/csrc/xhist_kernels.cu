@@ -16,6 +16,7 @@
 // xhist_k_f32.cu / xhist_k_f64.cu / xhist_k_i64.cu (parallel compilation); this file holds the small utility
 // kernels and the host-callable launchers.
 #include "xhist_kernels.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -93,6 +94,88 @@ __global__ void k_flush(uint4* buf, size_t n16) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) buf[i] = make_uint4(i, 0, 0, 0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// density (core.py:444-462): h = counts / bin_areas / rowsum, in that order, in float64.  bin_areas is the outer
+// product of the per-variable widths as numpy forms it with functools.reduce(np.multiply.outer, widths): a product of
+// two float32 operands is rounded to float32, anything else is a float64 product.  Counts arrive as int64 and are
+// rewritten in place as float64.  One warp per row (B <= 1024) or one CTA per row.
+// ---------------------------------------------------------------------------------------------
+struct XhkDensity {
+  const double* widths;              // device, all variables concatenated
+  int off[XHK_MAX_VARS];
+  int nb[XHK_MAX_VARS];
+  int f32[XHK_MAX_VARS];
+  int K;
+};
+
+__device__ __forceinline__ double density_area(const XhkDensity& q, long long b) {
+  int idx[XHK_MAX_VARS];
+  for (int k = q.K - 1; k >= 0; --k) { const long long t = b / q.nb[k]; idx[k] = static_cast<int>(b - t * q.nb[k]); b = t; }
+  double acc = q.widths[q.off[0] + idx[0]];
+  bool is32 = q.f32[0] != 0;
+  for (int k = 1; k < q.K; ++k) {
+    const double wk = q.widths[q.off[k] + idx[k]];
+    if (is32 && q.f32[k]) acc = static_cast<double>(__fmul_rn(static_cast<float>(acc), static_cast<float>(wk)));
+    else { acc = __dmul_rn(acc, wk); is32 = false; }
+  }
+  return acc;
+}
+
+template <bool COUNTS>
+__device__ __forceinline__ double density_load(const void* row, long long b) {
+  if (COUNTS) return static_cast<double>(static_cast<const long long*>(row)[b]);
+  return static_cast<const double*>(row)[b];
+}
+
+// rows of at most 1024 bins: one warp per row, sum and scale in one kernel
+template <bool COUNTS>
+__global__ void __launch_bounds__(256) k_density_rows(void* out, long long M, long long B, const __grid_constant__ XhkDensity q) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (long long r = static_cast<long long>(blockIdx.x) * nwarp + warp; r < M; r += static_cast<long long>(gridDim.x) * nwarp) {
+    unsigned char* row = static_cast<unsigned char*>(out) + static_cast<size_t>(r) * B * 8;
+    double fs = 0.0; long long is = 0;     // int64 counts add exactly; float64 sums in a fixed tree order
+    for (long long b = lane; b < B; b += 32) { if (COUNTS) is += reinterpret_cast<const long long*>(row)[b]; else fs += reinterpret_cast<const double*>(row)[b]; }
+    for (int o = 16; o > 0; o >>= 1) { fs += __shfl_xor_sync(0xffffffffu, fs, o); is += __shfl_xor_sync(0xffffffffu, is, o); }
+    const double total = COUNTS ? static_cast<double>(is) : fs;
+    for (long long b = lane; b < B; b += 32) {
+      const double v = density_load<COUNTS>(row, b);
+      reinterpret_cast<double*>(row)[b] = __ddiv_rn(__ddiv_rn(v, density_area(q, b)), total);
+    }
+  }
+}
+
+// longer rows: (1) chunk sums added into sums[r] (u64 for counts: exact; float64 otherwise), (2) flat scaling pass
+constexpr int kDensityChunk = 2048;
+template <bool COUNTS>
+__global__ void __launch_bounds__(256) k_density_sum(const void* out, long long B, int chunks, void* sums) {
+  __shared__ double s_f[8];
+  __shared__ long long s_i[8];
+  const long long r = blockIdx.x / chunks;
+  const long long b0 = static_cast<long long>(blockIdx.x % chunks) * kDensityChunk;
+  const long long b1 = b0 + kDensityChunk < B ? b0 + kDensityChunk : B;
+  const unsigned char* row = static_cast<const unsigned char*>(out) + static_cast<size_t>(r) * B * 8;
+  double fs = 0.0; long long is = 0;
+  for (long long b = b0 + threadIdx.x; b < b1; b += blockDim.x) { if (COUNTS) is += reinterpret_cast<const long long*>(row)[b]; else fs += reinterpret_cast<const double*>(row)[b]; }
+  for (int o = 16; o > 0; o >>= 1) { fs += __shfl_xor_sync(0xffffffffu, fs, o); is += __shfl_xor_sync(0xffffffffu, is, o); }
+  if ((threadIdx.x & 31) == 0) { s_f[threadIdx.x >> 5] = fs; s_i[threadIdx.x >> 5] = is; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (blockDim.x >> 5); ++i) { fs += s_f[i]; is += s_i[i]; }
+    if (COUNTS) atomicAdd(static_cast<unsigned long long*>(sums) + r, static_cast<unsigned long long>(is));
+    else atomicAdd(static_cast<double*>(sums) + r, fs);
+  }
+}
+template <bool COUNTS>
+__global__ void __launch_bounds__(256) k_density_scale(void* out, long long M, long long B, const void* sums, const __grid_constant__ XhkDensity q) {
+  const long long n = M * B, stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long r = i / B, b = i - r * B;
+    const double total = COUNTS ? static_cast<double>(static_cast<const long long*>(sums)[r]) : static_cast<const double*>(sums)[r];
+    const double v = density_load<COUNTS>(out, i);
+    static_cast<double*>(out)[i] = __ddiv_rn(__ddiv_rn(v, density_area(q, b)), total);
+  }
+}
+
 XhkHistKernel pick(int dtype, int w_dtype, int K, int mode) {
   return dtype == 1 ? xhk_pick_hist_f32(w_dtype, K, mode) : dtype == 2 ? xhk_pick_hist_f64(w_dtype, K, mode) : xhk_pick_hist_i64(w_dtype, K, mode);
 }
@@ -168,6 +251,30 @@ cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow*
 cudaError_t xhk_launch_zero_shared_rows(const XhkParams& p, const XhkLaunch& l) {
   if (l.w_dtype == 0) k_zero_shared_rows<unsigned long long><<<l.grid, 256, 0, l.stream>>>(p, l.grid);
   else k_zero_shared_rows<double><<<l.grid, 256, 0, l.stream>>>(p, l.grid);
+  return cudaGetLastError();
+}
+
+cudaError_t xhk_launch_density(void* out, long long M, long long B, int counts, const double* widths_dev, const int* nb, const int* f32,
+                               int K, void* sums_dev, cudaStream_t s) {
+  XhkDensity q;
+  q.widths = widths_dev; q.K = K;
+  int o = 0;
+  for (int k = 0; k < XHK_MAX_VARS; ++k) { q.off[k] = o; q.nb[k] = k < K ? nb[k] : 1; q.f32[k] = k < K ? f32[k] : 0; if (k < K) o += nb[k]; }
+  if (M <= 0 || B <= 0) return cudaSuccess;
+  if (B <= 1024) {
+    const int thr = 256, rows_per_cta = thr / 32;
+    const int grid = static_cast<int>(std::min<long long>((M + rows_per_cta - 1) / rows_per_cta, 148ll * 16));
+    if (counts) k_density_rows<true><<<grid, thr, 0, s>>>(out, M, B, q); else k_density_rows<false><<<grid, thr, 0, s>>>(out, M, B, q);
+    return cudaGetLastError();
+  }
+  // sums_dev holds M 8-byte slots
+  cudaError_t e = cudaMemsetAsync(sums_dev, 0, static_cast<size_t>(M) * 8, s);
+  if (e != cudaSuccess) return e;
+  const int chunks = static_cast<int>((B + kDensityChunk - 1) / kDensityChunk);
+  const unsigned g1 = static_cast<unsigned>(M * chunks);
+  const int g2 = static_cast<int>(std::min<long long>((M * B + 255) / 256, 148ll * 16));
+  if (counts) { k_density_sum<true><<<g1, 256, 0, s>>>(out, B, chunks, sums_dev); k_density_scale<true><<<g2, 256, 0, s>>>(out, M, B, sums_dev, q); }
+  else { k_density_sum<false><<<g1, 256, 0, s>>>(out, B, chunks, sums_dev); k_density_scale<false><<<g2, 256, 0, s>>>(out, M, B, sums_dev, q); }
   return cudaGetLastError();
 }
 

@@ -124,6 +124,10 @@ cudaError_t xhk_launch_hist_cols(const XhkParams& p, const XhkLaunch& l, long lo
 cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow* window_dev, int budget_bins, int budget32_bins, int n_probe);
 cudaError_t xhk_launch_zero_shared_rows(const XhkParams& p, const XhkLaunch& l);
 cudaError_t xhk_set_smem_limits(int max_optin);
+// density in place on the device: out[r][b] (int64 counts when `counts`, else float64) -> float64 h / area / rowsum
+// (sums_dev: M 8-byte slots of workspace, used when B > 1024)
+cudaError_t xhk_launch_density(void* out, long long M, long long B, int counts, const double* widths_dev, const int* nb, const int* f32,
+                               int K, void* sums_dev, cudaStream_t s);
 cudaError_t xhk_launch_fill(void* ptr, int dtype, long long n, unsigned long long seed, long long offset, int normal, cudaStream_t s);
 cudaError_t xhk_launch_minmax(const void* data, int dtype, long long n, double* out2_dev, cudaStream_t s);
 cudaError_t xhk_launch_flush(void* buf, size_t bytes, cudaStream_t s);

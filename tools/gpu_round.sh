@@ -9,7 +9,7 @@ tail -c 3000 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 1 --samples 2.5e8 > gpurun_out/${TAG}_ncu_launch.log 2>&1
 tail -3 gpurun_out/${TAG}_ncu_launch.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_hist -s 5 -c 1 -f -o gpurun_out/${TAG}_prof_hist \
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"k_hist<float, .int.3" -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_hist \
     python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -3 gpurun_out/${TAG}_ncu_full.log
 ls -la gpurun_out | tail -12

@@ -20,6 +20,7 @@ XH_FLAG_FORCE_SEARCH = 4
 XH_FLAG_FORCE_WINDOW = 8
 XH_FLAG_NO_FX32 = 16
 XH_FLAG_DENSITY = 32
+XH_FLAG_ALLREDUCE = 64
 XH_NCCL_UNIQUE_ID_BYTES = 128
 
 _ERRORS = {

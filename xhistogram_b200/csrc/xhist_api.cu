@@ -732,6 +732,11 @@ int hist_locked(Ctx* c, const xh_desc* d) {
       }
     }
   }
+  if (rc == XH_OK && (d->flags & XH_FLAG_ALLREDUCE) && out_bytes) {
+    // partial histograms of the ranks -> global histogram, in place, on the same stream (no host round trip)
+    if (!c->comm) return fail(XH_ERR_NCCL, "XH_FLAG_ALLREDUCE: no communicator on device %d (call xh_comm_init_rank first)", c->device);
+    NC(g_nccl.AllReduce(dev_out, dev_out, static_cast<size_t>(M * B), d->w_dtype == XH_NONE ? kNcclInt64 : kNcclFloat64, kNcclSum, c->comm, s));
+  }
   std::vector<double> wh;               // (stays alive until the stream is synchronised below)
   if (rc == XH_OK && (d->flags & XH_FLAG_DENSITY) && out_bytes) {
     // core.py:444-462 on the device, in place: counts / bin areas / row sums
@@ -844,7 +849,7 @@ int xh_hist_multi(const xh_desc* d, const int32_t* devices, int32_t n_dev) {
   if (!devices || n_dev < 1) return fail(XH_ERR_INVALID, "need at least one device");
   if (d->mem != XH_HOST || d->out_mem != XH_HOST) return fail(XH_ERR_INVALID, "xh_hist_multi takes host data and a host out");
   if (n_dev == 1) { xh_desc b = *d; b.device = devices[0]; return xh_hist(&b); }
-  if (d->flags & XH_FLAG_DENSITY) return fail(XH_ERR_UNSUPPORTED, "xh_hist_multi: the density is taken after the reduction, on the caller side");
+  if (d->flags & (XH_FLAG_DENSITY | XH_FLAG_ALLREDUCE)) return fail(XH_ERR_UNSUPPORTED, "xh_hist_multi reduces on its own; the density is taken on the caller side");
   if (d->n_inner > 1) return fail(XH_ERR_UNSUPPORTED, "xh_hist_multi does not take the column layout; shard the kept axis on the caller side");
   const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
   const size_t tsz = dsize(d->dtype), wsz = dsize(d->w_dtype);

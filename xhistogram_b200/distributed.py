@@ -165,11 +165,12 @@ def histogram(*local_args, bins=None, range=None, axis=None, weights=None, densi
         else:
             edges.append(_core._resolve_edges(a if _core.is_device_array(a) else np.asarray(a), b, r, None))
     if sharded_axis in red:
-        if isinstance(comm, NcclCommunicator) and _core.is_device_array(a0):
-            h = _device_partial_allreduce(local_args, weights, edges, axis, nd, comm)   # partial stays in HBM
-        else:
-            h, _ = _core.histogram(*local_args, bins=edges, axis=axis, weights=weights, density=False, block_size=block_size)
-            h = comm.allreduce_sum(np.ascontiguousarray(h))         # partial histograms -> global (core.py:439)
+        if isinstance(comm, NcclCommunicator):
+            # ONE native call: histogram kernels -> ncclAllReduce of the partials in HBM -> density -> D2H of the result
+            h = _fused_allreduce(local_args, weights, edges, axis, nd, comm, density)
+            return h, edges
+        h, _ = _core.histogram(*local_args, bins=edges, axis=axis, weights=weights, density=False, block_size=block_size)
+        h = comm.allreduce_sum(np.ascontiguousarray(h))         # partial histograms -> global (core.py:439)
     else:
         h, _ = _core.histogram(*local_args, bins=edges, axis=axis, weights=weights, density=False, block_size=block_size)
         if gather:
@@ -185,34 +186,22 @@ def histogram(*local_args, bins=None, range=None, axis=None, weights=None, densi
     return h, edges
 
 
-def _device_partial_allreduce(local_args, weights, edges, axis, nd, comm):
-    """Device-resident shard -> partial histogram in HBM -> ncclAllReduce in place -> one D2H of the result."""
-    from .device import DeviceArray
-
-    shape = _core.as_device_view(local_args[0])[1]
+def _fused_allreduce(local_args, weights, edges, axis, nd, comm, density):
+    """Shard (host or device resident) -> partial histogram in HBM -> ncclAllReduce in place -> density on the device
+    -> one D2H of the finished result, all inside one ``xh_hist`` call (XH_FLAG_ALLREDUCE [| XH_FLAG_DENSITY])."""
     ax = None if axis is None else [int(a) if a >= 0 else nd + int(a) for a in np.atleast_1d(axis)]
-    full = ax is None or set(ax) == set(_range(nd))
-    kept_shape = () if full else tuple(shape[i] for i in _range(nd) if i not in ax)
-    nbins = tuple(len(e) - 1 for e in edges)
-    M = int(np.prod(kept_shape, dtype=np.int64)) if kept_shape else 1
-    B = int(np.prod(nbins, dtype=np.int64))
-    out = _partial_buffer(comm.device, M * B)
     arrays = list(local_args) + ([weights] if weights is not None else [])
-    _core._bincount(*arrays, weights=weights is not None, axis=ax, bins=edges, _out_device=out)
-    comm.allreduce_device(out.ptr, M * B, weights is not None)
-    h = out.to_numpy()
-    h = h if weights is not None else h.view(np.int64)
-    return h.reshape(kept_shape + nbins)
-
-
-_partials = {}
-
-
-def _partial_buffer(device, n):
-    from .device import DeviceArray
-
-    buf = _partials.get(device)
-    if buf is None or buf.size < n:
-        buf = DeviceArray((n,), np.float64, device)
-        _partials[device] = buf
-    return buf if buf.size == n else buf.flat_slice(0, n)
+    if not _core.is_device_array(local_args[0]):
+        arrays = list(np.broadcast_arrays(*[np.asarray(a) for a in arrays]))
+    on_device = density and all(np.asarray(e).dtype in (np.float32, np.float64) for e in edges)
+    widths = [np.diff(e) for e in edges] if on_device else None
+    h = _core._bincount(*arrays, weights=weights is not None, axis=ax, bins=edges, _flags=_cabi.XH_FLAG_ALLREDUCE,
+                        _density_widths=widths, _devices=[comm.device])
+    if ax is not None:
+        h = h.squeeze(tuple(ax))
+    else:
+        h = h.reshape(h.shape[len(h.shape) - len(edges):])
+    if density and not on_device:
+        areas = functools.reduce(np.multiply.outer, [np.diff(e) for e in edges])
+        h = h / areas / h.sum(axis=tuple(_range(-len(edges), 0)), keepdims=True)
+    return h

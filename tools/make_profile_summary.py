@@ -36,13 +36,14 @@ tot = sum(a[1] for a in agg.values())
 out += ["| kernel | launches | total ms | share | longest launch ms |", "|---|---|---|---|---|"]
 for n, (c, t, m) in agg.items():
     out.append(f"| `{n}` | {c} | {t/1e6:.3f} | {100*t/tot:.1f}% | {m/1e6:.3f} |")
-big = [v for n, v in launches if "k_hist<float, 1" in n and v > 5e5]
+big = [v for n, v in launches if "k_hist<float, 3" in n and v > 4e5]      # the one-limb weighted kernel does the work of the step
 win = sorted(v for n, v in launches if "k_window" in n)
 if big and win:
     kb, kw = sum(big) / len(big), win[len(win) // 2]
     out += ["", f"Device-resident step (2.5e8 samples): `k_hist` {kb/1e6:.3f} ms per launch ({len(big)} launches), `k_window` median "
             f"{kw/1e3:.1f} us -> `k_hist` is {100*kb/(kb+kw):.1f}% of the step's kernel time (bench.py's roofline uses the CUDA-event "
             "time of both together).",
+            "`k_hist<float, 1, ...>` is the two-limb sibling launched next to it: the probe chose the one-limb form, so it returns at once (~3 us).",
             "The many short `k_hist` launches are the 8M-sample chunks of the end-to-end (host input) step; `k_fill` generates the synthetic inputs (untimed)."]
 open(os.path.join(P, f"{rnd}_launch_list.md"), "w").write("\n".join(out) + "\n")
 shutil.copy(os.path.join(G, f"{tag}_launches.csv"), os.path.join(P, f"{rnd}_launches.csv"))
@@ -60,7 +61,7 @@ keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 kname = g("Kernel Name") if "Kernel Name" in hdr else "k_hist"
 md = [f"# {rnd} — `ncu --set full` capture of the dominant kernel", "", f"Kernel: `{kname}`", "",
-      "Command: `ncu --set full --clock-control none --import-source on -k regex:k_hist -s 5 -c 1 python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1`",
+      "Command: `ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:\"k_hist<float, .int.3\" -s 3 -c 1 python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1`",
       "(config 3: 1e9 samples, 2 x fp32 + fp32 weights, 256x256 bins; one launch). The .ncu-rep is kept out of git (17 MB); the numbers below were",
       "read from it with `ncu -i ... --page raw --csv` / `--page source --csv` by `tools/make_profile_summary.py`.", "",
       "| metric | value | unit |", "|---|---|---|"]
@@ -77,8 +78,14 @@ traffic = float(g("dram__bytes_read.sum")) * mult[units[hdr.index("dram__bytes_r
 inst = float(g("smsp__inst_executed.sum"))
 md += ["", f"DRAM traffic per launch: {traffic/1e9:.4f} GB read+write vs 12.0005 GB algorithmic -> no re-reads (ratio {traffic/12000524288:.4f}).",
        f"Instructions: {inst:.3e} warp instructions = {inst*32/1e9:.1f} SASS instructions per sample; issue-active "
-       f"{g('smsp__issue_active.avg.pct_of_peak_sustained_active')} % -> the kernel is bound by instruction issue, not by DRAM "
-       f"({g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')} % of DRAM peak).", "Tensor pipe: 0 % (by design: scatter/reduce)."]
+       f"{g('smsp__issue_active.avg.pct_of_peak_sustained_active')} %, DRAM at "
+       f"{g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')} % of its peak: neither saturated — the largest stall reason is long_scoreboard "
+       "(a warp waiting for its own 16-byte loads; 32 warps per SM is all the 64-register budget of a 1024-thread CTA allows).",
+       "Tensor pipe: 0 % (by design: scatter/reduce)."]
+for k in ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+          "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"):
+    if k in hdr:
+        md.append(f"Pipe `{k.split('pipe_')[1].split('.')[0]}`: {float(g(k)):.1f} % of peak.")
 rows = list(csv.reader(open(os.path.join(G, f"{tag}_source.csv")))); h2 = rows[1]
 ia = h2.index("Source"); ie = h2.index("Instructions Executed"); iss = h2.index("Warp Stall Sampling (All Samples)")
 ops = collections.Counter(); tot = 0; body = []

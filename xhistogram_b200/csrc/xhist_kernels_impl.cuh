@@ -72,27 +72,39 @@ __device__ __forceinline__ bool uniform_guess(const XhkParams& p, int k, T x, in
   return (f >= Consts<T>::get(p, k, XHK_C_DELTA)) & (f <= Consts<T>::get(p, k, XHK_C_OMD));
 }
 
-// floor(t) as a T and as an int, for the branch-free fast path.  fp32: the integer part sits in the mantissa of
-// t + 1.5 * 2^23 rounded DOWN (valid for |t| < 2^22; beyond that — also NaN / inf — the integer lands outside
-// [0, 2^22) and the window test of the caller rejects it), so no F2I / I2F conversion is needed.
-template <typename T> struct FloorSplit;
-// run() returns floor(t) + kBias as the int (the caller folds kBias into its window offset).
-template <> struct FloorSplit<float> {
+// Fast path: r = t - 0.5 is split into rint(r) (as a T, and as an int with a bias) so that d = r - rint(r) is
+// frac(t) - 0.5 — the certainty test is |d| <= chalf — and rint(r) == floor(t) whenever the sample is certain.  The
+// integer sits in the mantissa of r + 1.5 * 2^23 (fp32) / 1.5 * 2^52 (fp64): no F2I / I2F conversion.  Outside the
+// valid range (|r| >= 2^22 resp. 2^31, NaN, inf) ok() is false or the integer lands outside [0, 2^22), where the
+// window test of the caller rejects it (bin counts on this path are <= 2^21).
+template <typename T> struct RoundSplit;
+template <> struct RoundSplit<float> {
   static constexpr int kBias = 0x4B400000;
-  static __device__ __forceinline__ void run(float t, float& jf, int& jraw) {
-    const float s = __fadd_rd(t, 12582912.0f);
+  static __device__ __forceinline__ void run(float r, float& jf, int& jraw) {
+    const float s = r + 12582912.0f;
     jf = s - 12582912.0f;
     jraw = __float_as_int(s);
   }
+  static __device__ __forceinline__ bool ok(float) { return true; }
 };
-template <> struct FloorSplit<double> {
+template <> struct RoundSplit<double> {
   static constexpr int kBias = 0;
-  static __device__ __forceinline__ void run(double t, double& jf, int& jraw) { jraw = __double2int_rd(t); jf = static_cast<double>(jraw); }
+  static __device__ __forceinline__ void run(double r, double& jf, int& jraw) {
+    const double s = r + 6755399441055744.0;
+    jf = s - 6755399441055744.0;
+    jraw = __double2loint(s);
+  }
+  // 0 <= rint(r) < 2^32  <=>  the high word of s is that of 1.5 * 2^52 (checked on the recomputed s: same value)
+  static __device__ __forceinline__ bool ok(double r) { return __double2hiint(r + 6755399441055744.0) == 0x43380000; }
 };
-template <> struct FloorSplit<long long> {   // never used (no uniform path for int64)
+template <> struct RoundSplit<long long> {   // never used (no uniform path for int64)
   static constexpr int kBias = 0;
-  static __device__ __forceinline__ void run(long long t, long long& jf, int& jraw) { jraw = static_cast<int>(t); jf = t; }
+  static __device__ __forceinline__ void run(long long r, long long& jf, int& jraw) { jraw = static_cast<int>(r); jf = r; }
+  static __device__ __forceinline__ bool ok(long long) { return true; }
 };
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ long long fma_t(long long a, long long b, long long c) { return a * b + c; }
 // keep a loop-invariant value in its register (under the 64-register cap ptxas otherwise rematerialises whole address
 // chains inside the hot loop)
 __device__ __forceinline__ unsigned pin(unsigned v) { asm volatile("" : "+r"(v)); return v; }
@@ -332,6 +344,33 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       }
     }
   };
+  // Side path of the fused fast kernels (every variable has evenly spaced edges): the exact bin of ONE sample,
+  // straight-line.  floor(t) is within one bin of the truth (|t_hat - t| < delta / 2 < 1/16), so comparing x with the
+  // two staged edges around the candidate settles it — what numpy's own uniform-bin path does
+  // (_histograms_impl.py:851-863).  In range and inside the window -> shared add, in range outside -> global RED.
+  auto side_uniform = [&](const T (&x)[KMAX], WT wsel, int rowl, OT* out_row) {
+    bool ok = true, inwin = true; int wbin = rowl; long long gbin = 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        const T xx = x[k];
+        ok = ok & (xx >= Consts<T>::get(p, k, XHK_C_LO)) & (xx <= Consts<T>::get(p, k, XHK_C_HI));   // NaN: false (rule R3)
+        const int nb = p.nb[k];
+        int b = floor_to_int((xx - Consts<T>::get(p, k, XHK_C_E0)) * Consts<T>::get(p, k, XHK_C_INV));
+        b = max(0, min(b, nb - 1));
+        const T* ed = sedges + p.eoff[k];
+        if (xx < ed[b]) b = max(b - 1, 0);
+        else if (b + 1 < nb && xx >= ed[b + 1]) b += 1;      // (the last bin is right-inclusive: never past nb - 1)
+        const unsigned jw = static_cast<unsigned>(b - wlo[k]);
+        inwin = inwin & (jw < static_cast<unsigned>(wlen[k]));
+        wbin = wbin * wlen[k] + static_cast<int>(jw);
+        gbin = gbin * nb + b;
+      }
+    }
+    if (!ok) return;
+    if (inwin) shared_add1(wbin, wsel, out_row);
+    else global_add(out_row, gbin, static_cast<double>(wsel));
+  };
   auto shared_add4 = [&](const int (&wb)[4], const WT (&wv)[4], OT* out_row) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) if (wb[e] >= 0) shared_add1(wb[e], wv[e], out_row);
@@ -387,9 +426,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       constexpr int REC = static_cast<int>(sizeof(T)) * KMAX + (W == 0 ? 0 : static_cast<int>(sizeof(WT)));   // bytes per sample
       constexpr int U = (FAST && W == 0 && REC <= 8) ? 3 : (REC <= 12) ? 2 : 1;
       const float fx_mulp = pin(static_cast<float>(fx_mul) * 2.98023223876953125e-8f);   // fx32: fx_mul * 2^-25
-      int jbias[KMAX];          // fused fast path: window offset of floor(t) + FloorSplit::kBias
+      int jbias[KMAX];          // fused fast path: window offset of the bin number + RoundSplit::kBias
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) jbias[k] = wlo[k] + FloorSplit<T>::kBias;
+      for (int k = 0; k < KMAX; ++k) jbias[k] = wlo[k] + RoundSplit<T>::kBias;
       if constexpr (FAST && W == 0) {
         // ---- counts on the fast path: fused classify + RED, software-pipelined over U register slots of 4 samples
         // per array — a slot is refilled with the group U steps ahead as soon as it has been consumed, so a warp keeps
@@ -417,12 +456,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
               bool good = live; int wbin = local_row(head + 4 * gu + e);
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) {
-                const T t = (xv[u][k][e] - Consts<T>::get(p, k, XHK_C_E0)) * Consts<T>::get(p, k, XHK_C_INV);
+                const T r = fma_t(xv[u][k][e] - Consts<T>::get(p, k, XHK_C_E0), Consts<T>::get(p, k, XHK_C_INV), T(-0.5));
                 T jf; int jraw;
-                FloorSplit<T>::run(t, jf, jraw);
-                const T d = t - (jf + T(0.5));
+                RoundSplit<T>::run(r, jf, jraw);
+                const T d = r - jf;                                  // frac(t) - 0.5, exact
                 const unsigned jw = static_cast<unsigned>(jraw - jbias[k]);
-                good = good & (fabs(d) <= Consts<T>::get(p, k, XHK_C_CHALF)) & (jw < static_cast<unsigned>(wlen[k]));
+                good = good & (fabs(d) <= Consts<T>::get(p, k, XHK_C_CHALF)) & (jw < static_cast<unsigned>(wlen[k])) & RoundSplit<T>::ok(r);
                 wbin = wbin * wlen[k] + static_cast<int>(jw);
               }
               idx[e] = good ? static_cast<unsigned>(wbin) : trash;
@@ -443,18 +482,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
                   }
-                bool sure = true; long long gbin = 0;
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k) {
-                  int jx; const bool certain = uniform_guess<T>(p, k, x[k], jx);
-                  sure = sure & certain & (static_cast<unsigned>(jx) < static_cast<unsigned>(p.nb[k]));
-                  gbin = gbin * p.nb[k] + jx;
-                }
-                if (sure && !tiled && p.hist_mode != XHK_FULL) global_add(out_row, gbin, 1.0);
-                else {
-                  const int wbin = general_sample(x, 1.0, out_row, local_row(head + 4 * gu + se));
-                  if (wbin >= 0) shared_add1(wbin, WT(1), out_row);
-                }
+                side_uniform(x, WT(1), local_row(head + 4 * gu + se), out_row);
               }
             }
             load_slot(u, gu + static_cast<long long>(U) * nthr);
@@ -573,12 +601,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
               bool good = live; int wbin = local_row(head + 4 * (g + static_cast<long long>(u) * nthr) + e);
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) {
-                const T t = (xv[u][k][e] - Consts<T>::get(p, k, XHK_C_E0)) * Consts<T>::get(p, k, XHK_C_INV);
+                const T r = fma_t(xv[u][k][e] - Consts<T>::get(p, k, XHK_C_E0), Consts<T>::get(p, k, XHK_C_INV), T(-0.5));
                 T jf; int jraw;
-                FloorSplit<T>::run(t, jf, jraw);
-                const T d = t - (jf + T(0.5));
+                RoundSplit<T>::run(r, jf, jraw);
+                const T d = r - jf;                                  // frac(t) - 0.5, exact
                 const unsigned jw = static_cast<unsigned>(jraw - jbias[k]);
-                good = good & (fabs(d) <= Consts<T>::get(p, k, XHK_C_CHALF)) & (jw < static_cast<unsigned>(wlen[k]));
+                good = good & (fabs(d) <= Consts<T>::get(p, k, XHK_C_CHALF)) & (jw < static_cast<unsigned>(wlen[k])) & RoundSplit<T>::ok(r);
                 wbin = wbin * wlen[k] + static_cast<int>(jw);
               }
               idx[u][e] = good ? static_cast<unsigned>(wbin) : trash;
@@ -648,6 +676,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
                     for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
                     wsel = wv[u][e];
                   }
+              // (the straight-line side_uniform() of the count path measured UNSTABLE here: identical launches took
+              //  2.1 to 4.0 ms; with this call-based exact path they take 2.21 ms every time)
               bool sure = true; long long gbin = 0;
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) {

@@ -351,7 +351,7 @@ def main():
         except Exception:
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_hist<float, W=1 (fp32 weights), K=2>", "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
+                "kernel": "k_hist<float, W=3 (fp32 weights, one-limb fixed point), K=2, MODE=1> (+ probe, sibling, density: all kernels of the call)", "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                 "peak_source": peak_src}
 
     cpu = None

@@ -288,6 +288,33 @@ def test_multi_gpu_in_process(gpu_count):
     assert np.array_equal(h, O.histogram(xr, bins=e, axis=1)[0])
 
 
+def test_fused_allreduce_single_rank():
+    """distributed.histogram over an NCCL communicator of ONE rank: histogram kernels, ncclAllReduce, density and D2H
+    run as one xh_hist call (XH_FLAG_ALLREDUCE | XH_FLAG_DENSITY); with one rank the result is the local one."""
+    from xhistogram_b200 import distributed as D
+
+    r = np.random.default_rng(21)
+    x, y = r.standard_normal((6, 50_001)).astype(np.float32), r.standard_normal((6, 50_001)).astype(np.float32)
+    w = r.random((6, 50_001), dtype=np.float32)
+    e = [np.linspace(-4, 4, 65), np.linspace(-3, 3, 33)]
+    with pytest.raises(RuntimeError, match="communicator"):          # the flag needs xh_comm_init_rank first
+        core._bincount(x, y, weights=False, axis=[1], bins=e, _flags=_cabi.XH_FLAG_ALLREDUCE)
+    comm = D.NcclCommunicator(0, 0, 1, D.NcclCommunicator.create_unique_id())
+    try:
+        for kw in (dict(), dict(weights=w), dict(weights=w, density=True), dict(density=True)):
+            for axis in (1, None):
+                h, _ = D.histogram(x, y, bins=e, axis=axis, comm=comm, sharded_axis=1, **kw)
+                with np.errstate(all="ignore"):
+                    want, _ = O.histogram(x, y, bins=e, axis=axis, **kw)
+                assert h.shape == want.shape
+                assert_hist_equal(h, want, rtol=1e-6)
+        xd, yd, wd = (DeviceArray.from_numpy(a.reshape(-1)) for a in (x, y, w))
+        h, _ = D.histogram(xd, yd, bins=e, weights=wd, density=True, comm=comm, sharded_axis=0)
+        assert_hist_equal(h, O.histogram(x.reshape(-1), y.reshape(-1), bins=e, weights=w.reshape(-1), density=True)[0], rtol=1e-6)
+    finally:
+        comm.close()
+
+
 @pytest.mark.parametrize("kind", ["wide_dynamic_range", "full_mantissa_f64", "negative_mixed", "all_zero", "huge", "tiny", "inf_nan_inside"])
 def test_weight_accumulation_modes(kind):
     """Weights that exercise the fixed-point scale selection, its float64 fallback and the inexact-weight spill."""

@@ -583,12 +583,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
                                             local_row(head + 4 * (g + static_cast<long long>(idx >> 2) * nthr) + (idx & 3)));
             if (wbin >= 0) shared_add1(wbin, wsel, out_row);
           }
-        } else if constexpr (FAST && (W == 0 || W == 3)) {
-          // ---- fused classify + accumulate (counts and one-limb weights).  Built to stay off the half-rate ALU
-          // pipe, which bounds this kernel: floor(t) from the mantissa trick (FADDs), certainty as ONE compare
-          // |t - (floor(t) + 0.5)| <= chalf, `live` as the seed of the predicate chain, no per-sample masks.  A sample
-          // that is not (certain and inside the window) adds nothing here (zero into a trash slot) and is picked up
-          // by the side loop below; idx == trash is how it is recognised there.
+        } else if constexpr (FAST && W == 3) {
+          // ---- one-limb weights on the fast path: fused classify + accumulate (the count path above explains the
+          // classification).  Both slots are loaded at the top of the iteration, classified and added (4 ATOMS back to
+          // back per slot), then ONE side loop serves the U * 4 samples.  A sample that is not (certain and inside
+          // the window) adds its value to a trash slot and is picked up by the side loop; idx < 0 marks it.
           unsigned idx[U][4];
           unsigned worst = 0;
 #pragma unroll
@@ -610,18 +609,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
                 wbin = wbin * wlen[k] + static_cast<int>(jw);
               }
               idx[u][e] = good ? static_cast<unsigned>(wbin) : trash;
-              if constexpr (W == 3) {
-                // v = round(clamp(w * 2^s, 0, 2^25)); the clamp rides on the multiplier (FMUL.SAT).  A sample that
-                // is not `good` adds its v to the trash slot (never read; checks below skip it)
-                const float we = wv[u][e];
-                vv[e] = __float2uint_rn(__saturatef(we * fx_mulp) * 33554432.0f);
-                any_rare = any_rare | (static_cast<float>(vv[e]) != we * static_cast<float>(fx_mul));
-              }
+              // v = round(clamp(w * 2^s, 0, 2^25)); the clamp rides on the multiplier (FMUL.SAT).  A sample that
+              // is not `good` adds its v to the trash slot (never read; checks below skip it)
+              const float we = wv[u][e];
+              vv[e] = __float2uint_rn(__saturatef(we * fx_mulp) * 33554432.0f);
+              any_rare = any_rare | (static_cast<float>(vv[e]) != we * static_cast<float>(fx_mul));   // (NaN: true)
             }
-            if constexpr (W == 0) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) reds_add_u32(sh_lo + 4u * idx[u][e], 1u);
-            } else {
+            {
 #pragma unroll
               for (int e = 0; e < 4; ++e) old[e] = atoms_add_u32(sh_lo + 4u * idx[u][e], vv[e]);
               // v < 2^26: the limb wrapped iff its top bit went from 1 to 0.  A wrap is worth 2^32 * 2^-s and goes

@@ -5,6 +5,10 @@
 #include "xhist_kernels.cuh"
 #include <type_traits>
 
+#ifndef XH_CHEAP_SIDE_W3
+#define XH_CHEAP_SIDE_W3 0
+#endif
+
 namespace {
 
 constexpr int kMaxThreads = XHK_THREADS;
@@ -670,6 +674,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
                     for (int k = 0; k < KMAX; ++k) x[k] = xv[u][k][e];
                     wsel = wv[u][e];
                   }
+#if XH_CHEAP_SIDE_W3
+              // experiment switch (make EXTRA=-DXH_CHEAP_SIDE_W3=1, tools/erratic_probe.sh): fast at best (2.10 ms, 0.87 of
+              // the HBM peak on config 3) but erratic, identical launches take 2.1 to 4.3 ms; see DESIGN.md section 8
+              side_uniform(x, wsel, local_row(head + 4 * (g + static_cast<long long>(sidx >> 2) * nthr) + (sidx & 3)), out_row);
+#else
               // (the straight-line side_uniform() of the count path measured UNSTABLE here: identical launches took
               //  2.1 to 4.0 ms; with this call-based exact path they take 2.21 ms every time)
               bool sure = true; long long gbin = 0;
@@ -685,6 +694,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
                                                 local_row(head + 4 * (g + static_cast<long long>(sidx >> 2) * nthr) + (sidx & 3)));
                 if (wbin >= 0) shared_add1(wbin, wsel, out_row);
               }
+#endif
             }
           }
           continue;   // (the generic accumulation below serves the other forms)

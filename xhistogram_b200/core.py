@@ -187,6 +187,7 @@ def _resolve_edges(a, bins, range_, weights):
 # the seam: one block -> one C-ABI call (reference: _bincount, core.py:197-247)
 # --------------------------------------------------------------------------------------------
 _default_dev = 0
+_timing_sink = None   # a list: every native call appends the device time of its kernels (CUDA events on the library stream, ms)
 _debug_flags = 0   # XH_FLAG_FORCE_* bits OR-ed into every call (tests exercise each kernel path with them)
 
 
@@ -400,6 +401,8 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
             return out
         d.out = out.ctypes.data
     ms = C.c_float(0.0)
+    if timing is None and _timing_sink is not None:
+        timing = {}
     if timing is not None:
         d.kernel_ms = C.pointer(ms)
     if devices is not None and len(devices) > 1:
@@ -409,6 +412,8 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
         _cabi.check(_cabi.lib().xh_hist(C.byref(d)), "xh_hist")
     if timing is not None:
         timing["kernel_ms"] = ms.value
+        if _timing_sink is not None:
+            _timing_sink.append(ms.value)
     return out
 
 

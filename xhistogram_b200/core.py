@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
+import math
 from collections.abc import Iterable
 
 import numpy as np
@@ -152,7 +153,7 @@ def _minmax(a):
     mn, mx = C.c_double(), C.c_double()
     if is_device_array(a):
         ptr, shape, dt, dev = as_device_view(a)
-        n, mem = int(np.prod(shape, dtype=np.int64)), _cabi.XH_DEVICE
+        n, mem = int(math.prod(shape)), _cabi.XH_DEVICE
     else:
         a = np.ascontiguousarray(a)
         ptr, dt, dev, n, mem = a.ctypes.data, a.dtype, _default_device(), a.size, _cabi.XH_HOST
@@ -164,7 +165,7 @@ def _resolve_edges(a, bins, range_, weights):
     """Bin edges of one variable, identical to ``np.histogram_bin_edges(a, bins, range, weights)``."""
     device = is_device_array(a)
     dt = as_device_view(a)[2] if device else a.dtype
-    size = int(np.prod(as_device_view(a)[1], dtype=np.int64)) if device else a.size
+    size = int(math.prod(as_device_view(a)[1])) if device else a.size
     if isinstance(bins, str):
         if device:
             raise TypeError("string bin estimators need host data; pass explicit bins or an int for device arrays")
@@ -229,9 +230,9 @@ def _column_layout(shape, axis):
     ax = sorted(axis)
     if not ax or ax != list(_range(ax[0], ax[-1] + 1)) or ax[-1] == len(shape) - 1:
         return None
-    outer = int(np.prod(shape[: ax[0]], dtype=np.int64))
-    n = int(np.prod(shape[ax[0]: ax[-1] + 1], dtype=np.int64))
-    inner = int(np.prod(shape[ax[-1] + 1:], dtype=np.int64))
+    outer = int(math.prod(shape[: ax[0]]))
+    n = int(math.prod(shape[ax[0]: ax[-1] + 1]))
+    inner = int(math.prod(shape[ax[-1] + 1:]))
     if inner < _MIN_INNER_COLUMNS or n == 0:
         return None
     return outer, n, inner
@@ -245,8 +246,8 @@ def _rows_view(a, axis, full):
     nd = a.ndim
     kept = [i for i in _range(nd) if i not in axis]
     moved = np.transpose(a, kept + list(axis))          # np.moveaxis(a, axis, range(-len(axis), 0)), core.py:218-219
-    M = int(np.prod([a.shape[i] for i in kept], dtype=np.int64))
-    N = int(np.prod([a.shape[i] for i in axis], dtype=np.int64))
+    M = int(math.prod([a.shape[i] for i in kept]))
+    N = int(math.prod([a.shape[i] for i in axis]))
     if M > 1 and all(moved.strides[i] == 0 or moved.shape[i] == 1 for i in _range(len(kept))):
         # broadcast over every kept axis (e.g. weights of shape (1, ncols)): pass one row, stride 0
         row = np.ascontiguousarray(moved[(0,) * len(kept)]).reshape(1, N)
@@ -287,10 +288,10 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
             raise TypeError("device inputs must share one dtype (float32 or float64)")
         n_inner = 0
         if full:
-            M, N = 1, int(np.prod(shape, dtype=np.int64))
+            M, N = 1, int(math.prod(shape))
         elif sorted(axis) == list(_range(nd - len(axis), nd)):
-            N = int(np.prod(shape[nd - len(axis):], dtype=np.int64))
-            M = int(np.prod(shape[: nd - len(axis)], dtype=np.int64))
+            N = int(math.prod(shape[nd - len(axis):]))
+            M = int(math.prod(shape[: nd - len(axis)]))
         else:
             col = _column_layout(shape, axis)
             if col is None:
@@ -388,7 +389,7 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
             d.widths[k] = wd.ctypes.data_as(C.POINTER(C.c_double))
             d.widths_f32[k] = 1 if np.asarray(density_widths[k]).dtype == np.float32 else 0
             keep.append(wd)
-    B = int(np.prod([len(b) - 1 for b in bins], dtype=np.int64))
+    B = int(math.prod([len(b) - 1 for b in bins]))
     if out_device is not None:
         if out_device.size != M * B or out_device.dtype.itemsize != 8:
             raise ValueError("device output buffer has the wrong size")

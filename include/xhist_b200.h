@@ -55,6 +55,8 @@ typedef enum xh_mem { XH_HOST = 0, XH_DEVICE = 1 } xh_mem;
                                    (xh_comm_init_rank) with ncclAllReduce before the density / the copy to `out`:
                                    histogram kernels, collective, density and D2H are one stream-ordered call — the
                                    role of dask's blockwise + .sum in core.py:429-439                              */
+#define XH_FLAG_ASYNC 128u      /* device data and device out only: return once the work is enqueued on the stream; `out`
+                                   is valid in stream order (xh_sync, or any later call on the same stream, orders after it) */
 #define XH_FLAG_DENSITY 32u     /* finish the density on the device (core.py:444-462): out becomes float64
                                    counts / bin areas / row sum, also without weights; needs widths[]         */
 
@@ -121,6 +123,10 @@ int xh_device_info(int device, int* sm_count, int* smem_optin_bytes, int64_t* to
 /* the hot path ------------------------------------------------------------------------ */
 int xh_hist(const xh_desc* d);                          /* replaces core.py:137-194 for one block */
 
+/* Host-side phase clock of the calling thread's last xh_hist, microseconds since entry: [0] edge tables ready (cache
+ * hit or prepared + uploaded), [1] all work enqueued, [2] stream synchronised, [3] return.  For overhead accounting.  */
+int xh_last_call_phases(double* us4);
+
 /* Block-partitioned form: the same request sharded over `n_dev` devices of this process
  * (rows when n_rows >= n_dev, else columns) and, when columns are sharded, combined with
  * ncclAllReduce(sum) — the role dask's blockwise + .sum plays in core.py:429-439.
@@ -139,6 +145,13 @@ int xh_host_free(void* ptr);
 int xh_memcpy(int device, void* dst, const void* src, size_t bytes, int dst_mem, int src_mem);
 int xh_memset(int device, void* dst, int value, size_t bytes);
 int xh_sync(int device);
+/* Order the library stream after the work already enqueued on `producer_stream` (a cudaStream_t; 1 / 2 = legacy /
+ * per-thread default stream): the synchronisation a __cuda_array_interface__ consumer owes its exporter.            */
+int xh_stream_wait(int device, void* producer_stream);
+/* dst = C-contiguous copy of transpose(src, perm) for an ndim-dimensional device array of 4- or 8-byte elements,
+ * enqueued on the library stream.  Replaces the host copy np.moveaxis(...).reshape(...) of core.py:218-226 for
+ * device-resident inputs whose reduce axes neither trail nor form one leading block.                              */
+int xh_permute(int device, const void* src, void* dst, int elem_size, int ndim, const int64_t* shape, const int32_t* perm);
 
 /* synthetic data (counter-based: element i depends only on (seed, offset+i)) ---------- */
 int xh_fill_normal(int device, void* ptr, int dtype, int64_t n, uint64_t seed, int64_t offset);

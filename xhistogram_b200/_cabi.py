@@ -21,6 +21,7 @@ XH_FLAG_FORCE_WINDOW = 8
 XH_FLAG_NO_FX32 = 16
 XH_FLAG_DENSITY = 32
 XH_FLAG_ALLREDUCE = 64
+XH_FLAG_ASYNC = 128
 XH_NCCL_UNIQUE_ID_BYTES = 128
 
 _ERRORS = {
@@ -77,6 +78,7 @@ PROTOTYPES = {
     "xh_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
     "xh_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "xh_hist": (C.c_int, [C.POINTER(XhDesc)]),
+    "xh_last_call_phases": (C.c_int, [C.POINTER(C.c_double)]),
     "xh_hist_multi": (C.c_int, [C.POINTER(XhDesc), C.POINTER(C.c_int32), C.c_int32]),
     "xh_minmax": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "xh_malloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -86,6 +88,8 @@ PROTOTYPES = {
     "xh_memcpy": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     "xh_memset": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_size_t]),
     "xh_sync": (C.c_int, [C.c_int]),
+    "xh_stream_wait": (C.c_int, [C.c_int, C.c_void_p]),
+    "xh_permute": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "xh_fill_normal": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_int64]),
     "xh_fill_uniform": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_int64]),
     "xh_timer_start": (C.c_int, [C.c_int]),

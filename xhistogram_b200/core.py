@@ -142,7 +142,13 @@ def _as_float_weights(w):
 
 
 def _xh_dtype(dt):
-    return _cabi.XH_F32 if np.dtype(dt) == np.float32 else _cabi.XH_F64
+    """xh_dtype of a float32/float64 array; anything else is a caller error (never reinterpreted)."""
+    dt = np.dtype(dt)
+    if dt == np.float32:
+        return _cabi.XH_F32
+    if dt == np.float64:
+        return _cabi.XH_F64
+    raise TypeError(f"the device path takes float32 or float64 arrays, got {dt}")
 
 
 # --------------------------------------------------------------------------------------------
@@ -156,6 +162,8 @@ def _minmax(a):
         n, mem = int(math.prod(shape)), _cabi.XH_DEVICE
     else:
         a = np.ascontiguousarray(a)
+        if a.dtype != np.float32 and a.dtype != np.float64:
+            return float(a.min()), float(a.max())        # non-float host data: numpy's own pass (as np.histogram_bin_edges does)
         ptr, dt, dev, n, mem = a.ctypes.data, a.dtype, _default_device(), a.size, _cabi.XH_HOST
     _cabi.check(_cabi.lib().xh_minmax(dev, ptr, _xh_dtype(dt), mem, n, C.byref(mn), C.byref(mx)), "xh_minmax")
     return mn.value, mx.value
@@ -163,6 +171,11 @@ def _minmax(a):
 
 def _resolve_edges(a, bins, range_, weights):
     """Bin edges of one variable, identical to ``np.histogram_bin_edges(a, bins, range, weights)``."""
+    if isinstance(bins, np.ndarray) and bins.ndim == 1 and bins.size >= 2 and bins.dtype.kind in "fiu":
+        # explicit edges: np.histogram_bin_edges returns them as they are after this check (_histograms_impl.py:427-431)
+        if (bins[:-1] > bins[1:]).any():
+            raise ValueError("`bins` must increase monotonically, when an array")
+        return bins
     device = is_device_array(a)
     dt = as_device_view(a)[2] if device else a.dtype
     size = int(math.prod(as_device_view(a)[1])) if device else a.size
@@ -279,31 +292,8 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
     nbins = tuple(len(b) - 1 for b in bins)
 
     if device_inputs:
-        views = [as_device_view(a) for a in all_arrays]
-        wview = as_device_view(w) if w is not None else None
-        for v in views + ([wview] if wview else []):
-            if v[1] != shape:
-                raise ValueError("device inputs must all have the same shape (no broadcasting on the device path)")
-        if len({v[2] for v in views}) != 1:
-            raise TypeError("device inputs must share one dtype (float32 or float64)")
-        n_inner = 0
-        if full:
-            M, N = 1, int(math.prod(shape))
-        elif sorted(axis) == list(_range(nd - len(axis), nd)):
-            N = int(math.prod(shape[nd - len(axis):]))
-            M = int(math.prod(shape[: nd - len(axis)]))
-        else:
-            col = _column_layout(shape, axis)
-            if col is None:
-                raise NotImplementedError("device inputs support reducing one contiguous block of axes: the trailing axes, "
-                                          f"or leading/middle axes followed by at least {_MIN_INNER_COLUMNS} kept columns")
-            outer, N, n_inner = col
-            M = outer * n_inner
-        dev = views[0][3]
-        out = _device_call(views, wview, bins, M, N, dev, _flags, _timing, _out_device, n_inner, _density_widths)
-        if _out_device is not None:
-            return out                                       # DeviceArray (M * prod(bins)), stays in HBM
-        return out.reshape(kept_axes_shape + nbins)
+        return _bincount_device(all_arrays, w, shape, nd, full, axis, bins, kept_axes_shape, nbins,
+                                _flags, _timing, _out_device, _density_widths)
 
     raw = [np.asarray(a) for a in all_arrays]
     iplan = _int64_plan(raw, bins)
@@ -322,15 +312,106 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
         if all(a.shape == tuple(shape) and a.flags.c_contiguous for a in everything):
             outer, N, n_inner = col
             wdt = _xh_dtype(w.dtype) if w is not None else _cabi.XH_NONE
-            out = _desc_call(data, [N] * len(data), w, N if w is not None else 0, bins, outer * n_inner, N, xdt_of(iplan, data), wdt,
-                             _cabi.XH_HOST, _default_device(), None, _flags, _timing, None, n_inner, _density_widths)
-            return out.reshape(kept_axes_shape + nbins)
+            dev = _devices[0] if _devices else _default_device()
+            try:
+                out = _desc_call(data, [N] * len(data), w, N if w is not None else 0, bins, outer * n_inner, N, xdt_of(iplan, data), wdt,
+                                 _cabi.XH_HOST, dev, None, _flags, _timing, None, n_inner, _density_widths)
+                return out.reshape(kept_axes_shape + nbins)
+            except NotImplementedError:
+                # the column kernel keeps one private histogram per column in shared memory; bin spaces too large for
+                # that take the row layout below (a transposing copy, as in the reference, then the windowed row kernel).
+                # Under XH_FLAG_ALLREDUCE every rank fails the same way (same bins), before any collective is entered.
+                pass
     rows = [_rows_view(a, ax, full) for a in data]
     M, N = rows[0][2], rows[0][3]
     wrow = _rows_view(w, ax, full) if w is not None else None
     xdt = xdt_of(iplan, data)
     out = _host_call([r[0] for r in rows], [r[1] for r in rows], wrow, bins, M, N, xdt, _devices, _flags, _timing, _density_widths)
     return out.reshape(kept_axes_shape + nbins)
+
+
+def _bincount_device(arrays, w, shape, nd, full, axis, bins, kept_axes_shape, nbins, flags, timing, out_device, density_widths):
+    """Device-resident block.  Reduced axes may be any subset: trailing axes are read in place as rows, one contiguous
+    block of leading/middle axes in place as columns (when the bin space fits the column kernel), anything else is
+    brought to row layout by a transposing copy ON THE DEVICE (xh_permute) — the reference does the same copy on the
+    host (np.moveaxis + reshape, core.py:218-226)."""
+    views = [as_device_view(a) for a in arrays]
+    wview = as_device_view(w) if w is not None else None
+    for v in views + ([wview] if wview else []):
+        if v[1] != shape:
+            raise ValueError("device inputs must all have the same shape (no broadcasting on the device path)")
+    if len({v[2] for v in views}) != 1:
+        raise TypeError("device inputs must share one dtype (float32 or float64)")
+    xdt = _xh_dtype(views[0][2])
+    wdt = _xh_dtype(wview[2]) if wview else _cabi.XH_NONE
+    dev = views[0][3]
+    _wait_for_producers(list(arrays) + ([w] if w is not None else []), dev)
+    ptrs = [v[0] for v in views]
+    wptr = wview[0] if wview else None
+
+    def call(ptrs, wptr, M, N, n_inner):
+        return _desc_call(ptrs, [N] * len(ptrs), wptr, N if wptr is not None else 0, bins, M, N, xdt, wdt,
+                          _cabi.XH_DEVICE, dev, None, flags, timing, out_device, n_inner, density_widths)
+
+    def finish(out):
+        return out if out_device is not None else out.reshape(kept_axes_shape + nbins)   # a DeviceArray stays flat, in HBM
+
+    if full:
+        return finish(call(ptrs, wptr, 1, int(math.prod(shape)), 0))
+    ax = sorted(axis)
+    if ax == list(_range(nd - len(ax), nd)):
+        N = int(math.prod(shape[nd - len(ax):]))
+        return finish(call(ptrs, wptr, int(math.prod(shape[: nd - len(ax)])), N, 0))
+    col = _column_layout(shape, ax)
+    if col is not None:
+        outer, N, n_inner = col
+        try:
+            return finish(call(ptrs, wptr, outer * n_inner, N, n_inner))
+        except NotImplementedError:
+            pass                                   # bin space too large for the column kernel: transpose below
+    kept = [i for i in _range(nd) if i not in ax]
+    perm = kept + ax
+    M = int(math.prod([shape[i] for i in kept]))
+    N = int(math.prod([shape[i] for i in ax]))
+    scratch = [_permuted_copy(v, perm, dev) for v in views + ([wview] if wview else [])]
+    try:
+        sp = [t.ptr for t in scratch]
+        return finish(call(sp[: len(views)], sp[len(views)] if wview else None, M, N, 0))
+    finally:
+        if out_device is not None and (flags & _cabi.XH_FLAG_ASYNC):
+            _cabi.check(_cabi.lib().xh_sync(dev), "xh_sync")      # the scratch copies must outlive the enqueued kernels
+        for t in scratch:
+            t.free()
+
+
+def _permuted_copy(view, perm, dev):
+    """C-contiguous device copy of ``transpose(view, perm)`` (xh_permute; replaces np.moveaxis + reshape of core.py:218-226)."""
+    ptr, shape, dt, _ = view
+    out = DeviceArray(tuple(shape[i] for i in perm), dt, dev)
+    nd = len(shape)
+    shp = (C.c_int64 * nd)(*shape)
+    prm = (C.c_int32 * nd)(*perm)
+    _cabi.check(_cabi.lib().xh_permute(dev, ptr, out.ptr, np.dtype(dt).itemsize, nd, shp, prm), "xh_permute")
+    return out
+
+
+def _wait_for_producers(arrays, dev):
+    """Order the library stream after the producers of foreign ``__cuda_array_interface__`` inputs.
+
+    Contract (CAI v3): an exporter that sets ``stream`` wants consumers to synchronise with that stream (1 = legacy
+    default stream, 2 = per-thread default stream, else a ``cudaStream_t``); the library stream then waits on an event
+    recorded there.  An exporter that sets no stream (version 2 objects, e.g. torch tensors) is assumed to enqueue on
+    the legacy default stream, which is waited on the same way.  ``DeviceArray`` buffers are only ever written by
+    synchronous library calls and need nothing.
+    """
+    streams = set()
+    for a in arrays:
+        if isinstance(a, DeviceArray):
+            continue
+        st = a.__cuda_array_interface__.get("stream", None)
+        streams.add(1 if st is None else int(st))
+    for st in streams:
+        _cabi.check(_cabi.lib().xh_stream_wait(dev, st), "xh_stream_wait")
 
 
 def xdt_of(iplan, data):
@@ -344,12 +425,16 @@ def _host_call(arrs, strides, wrow, bins, M, N, xdt, devices, flags, timing, den
                       devices[0] if devices else _default_device(), devices, flags, timing, density_widths=density_widths)
 
 
-def _device_call(views, wview, bins, M, N, dev, flags, timing, out_device=None, n_inner=0, density_widths=None):
-    ptrs = [v[0] for v in views]
-    wptr = wview[0] if wview else None
-    wdt = _xh_dtype(wview[2]) if wview else _cabi.XH_NONE
-    return _desc_call(ptrs, [N] * len(ptrs), wptr, N if wview else 0, bins, M, N, _xh_dtype(views[0][2]), wdt,
-                      _cabi.XH_DEVICE, dev, None, flags, timing, out_device, n_inner, density_widths)
+def _edge_pointer(b, want, ptype, keep):
+    """(pointer to a contiguous ``want``-typed copy of the edges, number of edges).  The copy is kept alive in ``keep``
+    for the duration of the call; edges that already are contiguous ``want`` arrays are passed as they are."""
+    e = b if (isinstance(b, np.ndarray) and b.dtype == want and b.flags.c_contiguous) else np.ascontiguousarray(b, dtype=want)
+    keep.append(e)
+    return C.cast(e.ctypes.data, ptype), e.size
+
+
+_PD = C.POINTER(C.c_double)
+_PI = C.POINTER(C.c_int64)
 
 
 def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing, out_device=None,
@@ -362,6 +447,7 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
     d.n_rows, d.n_cols = M, N
     d.n_inner = n_inner
     keep = []
+    B = 1
     for k in _range(K):
         if mem == _cabi.XH_HOST:
             d.data[k] = arrs[k].ctypes.data if arrs[k].size else None
@@ -369,13 +455,10 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
             d.data[k] = arrs[k]
         d.row_stride[k] = strides[k]
         if dtype == _cabi.XH_I64:
-            e = np.ascontiguousarray(bins[k], dtype=np.int64)
-            d.iedges[k] = e.ctypes.data_as(C.POINTER(C.c_int64))
+            d.iedges[k], d.n_edges[k] = _edge_pointer(bins[k], np.int64, _PI, keep)
         else:
-            e = np.ascontiguousarray(bins[k], dtype=np.float64)
-            d.edges[k] = e.ctypes.data_as(C.POINTER(C.c_double))
-        keep.append(e)
-        d.n_edges[k] = e.size
+            d.edges[k], d.n_edges[k] = _edge_pointer(bins[k], np.float64, _PD, keep)
+        B *= d.n_edges[k] - 1
     if w is not None:
         d.weights = (w.ctypes.data if w.size else None) if mem == _cabi.XH_HOST else w
         d.w_row_stride = wstride
@@ -385,32 +468,34 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
         # density on the device: widths as float64 values plus how numpy holds them (float32 products round to float32)
         d.flags |= _cabi.XH_FLAG_DENSITY
         for k in _range(K):
-            wd = np.ascontiguousarray(density_widths[k], dtype=np.float64)
-            d.widths[k] = wd.ctypes.data_as(C.POINTER(C.c_double))
-            d.widths_f32[k] = 1 if np.asarray(density_widths[k]).dtype == np.float32 else 0
-            keep.append(wd)
-    B = int(math.prod([len(b) - 1 for b in bins]))
+            d.widths[k], _ = _edge_pointer(density_widths[k], np.float64, _PD, keep)
+            d.widths_f32[k] = 1 if density_widths[k].dtype == np.float32 else 0
     if out_device is not None:
         if out_device.size != M * B or out_device.dtype.itemsize != 8:
             raise ValueError("device output buffer has the wrong size")
         out = out_device
         d.out, d.out_mem = out_device.ptr, _cabi.XH_DEVICE
     else:
+        if d.flags & _cabi.XH_FLAG_ASYNC:
+            raise ValueError("an asynchronous call needs a device output buffer")
         out = np.empty((M, B), dtype=np.int64 if (w is None and density_widths is None) else np.float64)
-        if M * N == 0 or B == 0:
+        if (M * N == 0 and not (d.flags & _cabi.XH_FLAG_ALLREDUCE)) or M * B == 0:
             out[...] = np.nan if (density_widths is not None and B) else 0      # 0 / area / 0, as numpy computes it
             return out
         d.out = out.ctypes.data
-    ms = C.c_float(0.0)
-    if timing is None and _timing_sink is not None:
+    ms = None
+    if timing is None and _timing_sink is not None and not (d.flags & _cabi.XH_FLAG_ASYNC):
         timing = {}
     if timing is not None:
+        ms = C.c_float(0.0)
         d.kernel_ms = C.pointer(ms)
     if devices is not None and len(devices) > 1:
         arr = (C.c_int32 * len(devices))(*devices)
         _cabi.check(_cabi.lib().xh_hist_multi(C.byref(d), arr, len(devices)), "xh_hist_multi")
     else:
-        _cabi.check(_cabi.lib().xh_hist(C.byref(d)), "xh_hist")
+        rc = _cabi.lib().xh_hist(C.byref(d))
+        if rc:
+            _cabi.check(rc, "xh_hist")
     if timing is not None:
         timing["kernel_ms"] = ms.value
         if _timing_sink is not None:
@@ -421,14 +506,70 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
 # --------------------------------------------------------------------------------------------
 # public entry point (reference: core.py:250-466)
 # --------------------------------------------------------------------------------------------
+def _normalise_axis(axis, ndim):
+    if axis is None:                                                 # core.py:341-352
+        return None
+    axis = np.atleast_1d(axis)
+    assert axis.ndim == 1
+    axis_normed = []
+    for ax in axis:
+        ax_positive = ax if ax >= 0 else ndim + ax
+        assert ax_positive < ndim, "axis must be less than ndim"
+        axis_normed.append(int(ax_positive))
+    return axis_normed
+
+
+def _histogram_device(args, bins, range, axis, weights, density, out):
+    """``histogram`` for device-resident inputs (``DeviceArray`` / ``__cuda_array_interface__``): nothing but metadata
+    is touched on the host.  With ``out`` (a float64/int64-sized ``DeviceArray``) the call only enqueues: the result
+    stays in HBM and is valid in stream order (``xh_sync`` or any later library call orders after it)."""
+    all_arrays = list(args) + ([weights] if weights is not None else [])
+    if not all(is_device_array(a) for a in all_arrays):
+        raise TypeError("cannot mix device-resident and host arrays in one call")
+    views = [as_device_view(a) for a in all_arrays]
+    for v in views:
+        _xh_dtype(v[2])                                              # float32 / float64 only: never reinterpret other dtypes
+    shape = views[0][1]
+    if any(v[1] != shape for v in views):
+        raise ValueError("device inputs must all have the same shape")
+    ndim, n_inputs = len(shape), len(args)
+    axis = _normalise_axis(axis, ndim)
+    bins = _ensure_correctly_formatted_bins(bins, n_inputs)
+    range = _ensure_correctly_formatted_range(range, n_inputs)
+    bins = [_resolve_edges(a, b, r, None) for a, b, r in zip(args, bins, range)]
+    for b in bins:
+        if b.dtype.kind not in "fiu":
+            raise TypeError(f"unsupported bin-edge dtype {b.dtype} for device-resident data")
+    nbins = tuple(len(b) - 1 for b in bins)
+    full = axis is None or set(axis) == set(_range(ndim))
+    kept_shape = () if full else tuple(shape[i] for i in _range(ndim) if i not in axis)
+    kept_axes_shape = (1,) * ndim if full else tuple(shape[i] if i not in axis else 1 for i in _range(ndim))
+    device_density = density and all(b.dtype.kind == "f" and b.dtype.itemsize in (4, 8) for b in bins)
+    if density and not device_density and out is not None:
+        raise TypeError("density=True with out= needs float bin edges")
+    widths = [np.diff(b) for b in bins] if device_density else None
+    flags = _cabi.XH_FLAG_ASYNC if out is not None else 0
+    h = _bincount_device(list(args), weights, shape, ndim, full, axis, bins, kept_axes_shape, nbins, flags, None,
+                         out.reshape(-1) if out is not None else None, widths)
+    if out is not None:
+        return out.reshape(kept_shape + nbins), bins
+    h = h.reshape(kept_shape + nbins)
+    if density and not device_density:
+        areas = functools.reduce(np.multiply.outer, [np.diff(b) for b in bins])
+        sums = h.sum(axis=tuple(_range(-n_inputs, 0)), keepdims=True)
+        h = h / areas / sums
+    return h, bins
+
+
 def histogram(*args, bins=None, range=None, axis=None, weights=None, density=False, block_size="auto",
-              devices=None):
+              devices=None, out=None):
     """Histogram applied along specified axis / axes — signature of ``xhistogram.core.histogram``.
 
-    Parameters are those of the reference (see its docstring, core.py:259-333).  ``devices``
-    (extension, optional): list of CUDA ordinals to shard a host-resident request over; rows
-    are split when enough rows are kept, otherwise the reduced axis is split and the partial
-    histograms are summed with NCCL.
+    Parameters are those of the reference (see its docstring, core.py:259-333).  Extensions, both optional:
+    ``devices`` — list of CUDA ordinals to shard a host-resident request over (rows are split when enough rows are
+    kept, otherwise the reduced axis is split and the partial histograms are summed with NCCL);
+    ``out`` — for device-resident inputs, a ``DeviceArray`` of 8-byte items that receives the result: the call
+    returns as soon as the work is enqueued and the result stays in HBM (``out.to_numpy()`` synchronises).
 
     Returns ``(hist, bin_edges)``: ``hist`` has the kept axes (original order) followed by one
     axis per argument; int64 counts, or float64 when ``weights`` or ``density`` is given.
@@ -437,11 +578,15 @@ def histogram(*args, bins=None, range=None, axis=None, weights=None, density=Fal
         raise TypeError("histogram() needs at least one array")
     if block_size is not None and block_size != "auto" and not isinstance(block_size, (int, np.integer)):
         raise TypeError("block_size must be None, an int or 'auto'")
+    if is_device_array(args[0]):
+        return _histogram_device(args, bins, range, axis, weights, density, out)
+    if out is not None:
+        raise TypeError("out= is for device-resident inputs")
     is_dask_array = any(_is_dask(a) for a in list(args) + [weights])
-    device_inputs = any(is_device_array(a) for a in list(args) + [weights])
-    if device_inputs and not all(is_device_array(a) for a in list(args) + ([weights] if weights is not None else [])):
+    device_inputs = False
+    if any(is_device_array(a) for a in list(args) + [weights]):
         raise TypeError("cannot mix device-resident and host arrays in one call")
-    if not is_dask_array and not device_inputs:
+    if not is_dask_array:
         args = tuple(np.asarray(a) for a in args)
         weights = None if weights is None else np.asarray(weights)
 
@@ -449,15 +594,7 @@ def histogram(*args, bins=None, range=None, axis=None, weights=None, density=Fal
     ndim = len(as_device_view(a0)[1]) if device_inputs else a0.ndim
     n_inputs = len(args)
 
-    if axis is not None:                                             # core.py:341-352
-        axis = np.atleast_1d(axis)
-        assert axis.ndim == 1
-        axis_normed = []
-        for ax in axis:
-            ax_positive = ax if ax >= 0 else ndim + ax
-            assert ax_positive < ndim, "axis must be less than ndim"
-            axis_normed.append(ax_positive)
-        axis = [int(i) for i in axis_normed]
+    axis = _normalise_axis(axis, ndim)
 
     all_arrays = list(args)
     has_weights = weights is not None

@@ -14,6 +14,8 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -24,6 +26,11 @@
 namespace {
 
 thread_local std::string g_err;
+// host-side phase clock of the calling thread's last xh_hist (microseconds since entry): [0] edge tables ready,
+// [1] everything enqueued, [2] stream synchronised, [3] return.  Read with xh_last_call_phases().
+thread_local double g_phase[4] = {0, 0, 0, 0};
+thread_local std::chrono::steady_clock::time_point g_t0;
+inline void phase_mark(int i) { g_phase[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - g_t0).count(); }
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -51,6 +58,7 @@ struct NcclApi {
   int (*CommInitAll)(void**, int, const int*) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -69,7 +77,7 @@ int nccl_load() {
   *reinterpret_cast<void**>(&g_nccl.field) = dlsym(h, name);                         \
   if (!g_nccl.field) return fail(XH_ERR_NCCL, "NCCL symbol %s missing", name);
   SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommInitAll, "ncclCommInitAll")
-  SYM(CommDestroy, "ncclCommDestroy") SYM(AllReduce, "ncclAllReduce") SYM(GroupStart, "ncclGroupStart")
+  SYM(CommDestroy, "ncclCommDestroy") SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(GroupStart, "ncclGroupStart")
   SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
   g_nccl.handle = h;
@@ -80,7 +88,7 @@ int nccl_load() {
     int r__ = (call);                                                                             \
     if (r__ != 0) return fail(XH_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__));    \
   } while (0)
-constexpr int kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0;
+constexpr int kNcclInt8 = 0, kNcclInt32 = 2, kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0, kNcclMin = 3;
 
 // ------------------------------------------------------------------------------------------ context
 struct Ctx {
@@ -107,10 +115,31 @@ struct Ctx {
   void* outbuf = nullptr;            // device histogram when the caller's out is host memory
   size_t outbuf_cap = 0;
   void* comm = nullptr;              // NCCL communicator (multi-process mode)
+  int comm_ranks = 0, comm_rank = 0;
+  // peer-memory reduction of small partial histograms (one rank per GPU, same node): every rank's symmetric buffer
+  // [flags | slot 0 | slot 1] is mapped into every other rank through CUDA IPC; see peer_allreduce()
+  struct Peer {
+    int state = 0;                   // 0 not tried, 1 usable, -1 unavailable (NCCL is used instead)
+    size_t cap = 0;                  // bytes per slot
+    unsigned char* local = nullptr;
+    unsigned char* mapped[XHK_MAX_PEERS] = {};
+    unsigned long long seq = 0;
+  } peer;
+  // caches (guarded by mu): prepared edge tables by edge content, probe verdicts by (tables, buffers, shape)
+  std::vector<struct PrepEntry*> preps;
+  struct Verdict* verdicts = nullptr;     // kVerdictSlots entries; entry i owns slot i of the two slabs below
+  unsigned char* vslab_dev = nullptr;     // device: per slot [XhkWindow][u64 slow-path counter at +kVerdictStatsOff]
+  unsigned char* vslab_host = nullptr;    // pinned mirror of the same
+  cudaEvent_t vev[32];
+  unsigned long long stamp = 0, next_prep_id = 1;
+  unsigned long long* dummy_stats = nullptr;   // device counter for launches that bypass the verdict cache
 };
+constexpr int kVerdictSlots = 32, kVerdictSlotBytes = 128, kVerdictStatsOff = 96;
+static_assert(sizeof(XhkWindow) <= kVerdictStatsOff, "verdict slot layout");
 
 std::mutex g_ctx_mu;
 std::map<int, Ctx*> g_ctx;
+struct Verdict* alloc_verdicts();
 
 int get_ctx(int device, Ctx** out) {
   std::lock_guard<std::mutex> lk(g_ctx_mu);
@@ -134,6 +163,13 @@ int get_ctx(int device, Ctx** out) {
   for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&c->copied[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->consumed[i], cudaEventDisableTiming)); }
   CU(cudaMalloc(&c->window, sizeof(XhkWindow)));
   CU(cudaMalloc(&c->minmax, 296 * 3 * sizeof(double)));
+  CU(cudaMalloc(&c->vslab_dev, kVerdictSlots * kVerdictSlotBytes + 64));
+  CU(cudaMemset(c->vslab_dev, 0, kVerdictSlots * kVerdictSlotBytes + 64));
+  c->dummy_stats = reinterpret_cast<unsigned long long*>(c->vslab_dev + kVerdictSlots * kVerdictSlotBytes);
+  CU(cudaHostAlloc(reinterpret_cast<void**>(&c->vslab_host), kVerdictSlots * kVerdictSlotBytes, cudaHostAllocPortable));
+  std::memset(c->vslab_host, 0, kVerdictSlots * kVerdictSlotBytes);
+  for (int i = 0; i < kVerdictSlots; ++i) CU(cudaEventCreateWithFlags(&c->vev[i], cudaEventDisableTiming));
+  c->verdicts = alloc_verdicts();
   CU(xhk_set_smem_limits(c->smem_optin - XHK_STATIC_SMEM));  // static shared memory of k_hist
   g_ctx[device] = c;
   *out = c;
@@ -274,7 +310,38 @@ struct Prep {
   std::vector<unsigned char> edge_host;   // effective edges followed (16-byte aligned) by the lookup tables
   size_t edges_al = 0;                     // shared-memory bytes of edges + tables
   size_t lut_dev_off = 0;                  // byte offset of the tables inside edge_host / the device buffer
-  mutable bool window_done = false;   // the shared-memory window is chosen on the first block of a call and reused
+  void* dev_edges = nullptr;               // device copy of edge_host (owned by the cache entry)
+};
+
+// A prepared set of bin edges, cached per device by edge CONTENT (dtype, counts, search flag, raw edge bytes): a repeat
+// call with the same edges skips the host preparation (effective edges, certainty margins, lookup tables) and the
+// upload.  The density widths of the last call with these edges are kept next to it.
+struct PrepEntry {
+  std::vector<unsigned char> key;
+  Prep pr;
+  unsigned long long id = 0, stamp = 0;
+  std::vector<double> widths;              // host copy of what dev_widths holds
+  double* dev_widths = nullptr;
+  size_t dev_widths_cap = 0;
+};
+
+// The verdict of the probe kernel (shared-memory window + fixed-point form of the weights) for one block, cached by
+// (edge tables, buffer addresses, shape).  Results never depend on it — a sample outside the window or a weight outside
+// the fixed-point form takes a slower exact path — so a stale verdict can only cost time.  That cost is watched:
+// k_hist counts the samples that took a slow path, and a verdict whose slow fraction grows well beyond what the
+// probing call saw is dropped (the next call probes again).
+struct Verdict {
+  bool used = false;
+  unsigned long long prep_id = 0, stamp = 0;
+  const void* data[XH_MAX_VARS]; const void* w = nullptr;
+  long long stride[XH_MAX_VARS]; long long wstride = 0, M = 0, N = 0, tile_n = 0;
+  int K = 0, dtype = 0, w_dtype = 0, tile_rows = 1, budget = 0, budget32 = 0;
+  unsigned flags = 0;
+  int state = 0;                 // 1: probe enqueued, host mirror not yet known to be valid; 2: host mirror valid
+  unsigned long long last_slow = 0, calls = 0;
+  long long samples_since = 0;
+  double base_frac = -1.0;       // slow fraction of the first checked interval
+  bool stats_pending = false;    // a copy of the counter to the host mirror has been enqueued since the last check
 };
 
 int prep_call(const xh_desc* d, Prep& pr) {
@@ -321,18 +388,61 @@ int prep_call(const xh_desc* d, Prep& pr) {
   return XH_OK;
 }
 
-int upload_edges(Ctx* c, const Prep& pr, cudaStream_t s) {
-  const size_t bytes = pr.edge_host.size();
-  if (bytes > c->edges_cap) {
-    if (c->edges) cudaFree(c->edges);
-    c->edges = nullptr; c->edges_cap = 0;
-    size_t cap = std::max<size_t>(bytes, 1 << 16);
-    CU(cudaMalloc(&c->edges, cap));
-    c->edges_cap = cap;
+// ---- caches ---------------------------------------------------------------------------------------------------
+constexpr size_t kMaxPreps = 16;
+
+std::vector<unsigned char> prep_key(const xh_desc* d) {
+  std::vector<unsigned char> k;
+  auto put = [&](const void* q, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(q); k.insert(k.end(), b, b + n); };
+  const int32_t head[3] = {d->dtype, d->n_vars, (d->flags & XH_FLAG_FORCE_SEARCH) ? 1 : 0};
+  put(head, sizeof head);
+  put(d->n_edges, sizeof(int32_t) * d->n_vars);
+  for (int i = 0; i < d->n_vars; ++i)
+    put(d->dtype == XH_I64 ? static_cast<const void*>(d->iedges[i]) : static_cast<const void*>(d->edges[i]), static_cast<size_t>(d->n_edges[i]) * 8);
+  return k;
+}
+
+void free_prep(PrepEntry* e) {
+  if (e->pr.dev_edges) cudaFree(e->pr.dev_edges);
+  if (e->dev_widths) cudaFree(e->dev_widths);
+  delete e;
+}
+
+// Prepared edges for this request: from the cache, or prepared now and uploaded (blocking: first use only).
+int lookup_prep(Ctx* c, const xh_desc* d, PrepEntry** out) {
+  std::vector<unsigned char> key = prep_key(d);
+  for (PrepEntry* e : c->preps)
+    if (e->key.size() == key.size() && std::memcmp(e->key.data(), key.data(), key.size()) == 0) { e->stamp = ++c->stamp; *out = e; return XH_OK; }
+  PrepEntry* e = new PrepEntry();
+  int rc = prep_call(d, e->pr);
+  if (rc) { delete e; return rc; }
+  const size_t bytes = std::max<size_t>(e->pr.edge_host.size(), 16);
+  cudaError_t ce = cudaMalloc(&e->pr.dev_edges, bytes);
+  if (ce == cudaSuccess && !e->pr.edge_host.empty()) ce = cudaMemcpy(e->pr.dev_edges, e->pr.edge_host.data(), e->pr.edge_host.size(), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { free_prep(e); return fail(ce == cudaErrorMemoryAllocation ? XH_ERR_NOMEM : XH_ERR_CUDA, "edge table upload: %s", cudaGetErrorString(ce)); }
+  e->key.swap(key);
+  e->id = c->next_prep_id++;
+  e->stamp = ++c->stamp;
+  if (c->preps.size() >= kMaxPreps) {
+    // evict the least recently used entry; kernels of earlier (asynchronous) calls may still read its tables
+    size_t lru = 0;
+    for (size_t i = 1; i < c->preps.size(); ++i) if (c->preps[i]->stamp < c->preps[lru]->stamp) lru = i;
+    cudaDeviceSynchronize();
+    for (int i = 0; i < kVerdictSlots; ++i) if (c->verdicts[i].used && c->verdicts[i].prep_id == c->preps[lru]->id) c->verdicts[i].used = false;
+    free_prep(c->preps[lru]);
+    c->preps.erase(c->preps.begin() + lru);
   }
-  CU(cudaMemcpyAsync(c->edges, pr.edge_host.data(), bytes, cudaMemcpyHostToDevice, s));
+  c->preps.push_back(e);
+  *out = e;
   return XH_OK;
 }
+
+Verdict* alloc_verdicts() { return new Verdict[kVerdictSlots]; }
+
+XhkWindow* verdict_dev(Ctx* c, int slot) { return reinterpret_cast<XhkWindow*>(c->vslab_dev + static_cast<size_t>(slot) * kVerdictSlotBytes); }
+const XhkWindow* verdict_host(Ctx* c, int slot) { return reinterpret_cast<const XhkWindow*>(c->vslab_host + static_cast<size_t>(slot) * kVerdictSlotBytes); }
+unsigned long long* verdict_stats_dev(Ctx* c, int slot) { return reinterpret_cast<unsigned long long*>(c->vslab_dev + static_cast<size_t>(slot) * kVerdictSlotBytes + kVerdictStatsOff); }
+unsigned long long verdict_stats_host(Ctx* c, int slot) { return *reinterpret_cast<volatile unsigned long long*>(c->vslab_host + static_cast<size_t>(slot) * kVerdictSlotBytes + kVerdictStatsOff); }
 
 // Launch plan of one block whose data/weights/out pointers are DEVICE pointers.
 // fx32 = true plans the k_hist<W = 3> sibling of an fp32-weighted block (4 bytes per shared bin instead of 8).
@@ -354,8 +464,9 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
   p.w = d->weights; p.wstride = d->w_row_stride;
   p.out = d->out;
   p.window = c->window;
-  p.edges = c->edges;
-  p.lut = reinterpret_cast<const unsigned short*>(static_cast<const unsigned char*>(c->edges) + pr.lut_dev_off);
+  p.edges = pr.dev_edges;
+  p.lut = reinterpret_cast<const unsigned short*>(static_cast<const unsigned char*>(pr.dev_edges) + pr.lut_dev_off);
+  p.stats = c->dummy_stats;
   const long long B = p.B;
 
   // shared-memory budget
@@ -421,33 +532,126 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
   return XH_OK;
 }
 
-// Enqueue zero-fill, window selection and the histogram kernel(s) of one planned block.  With an fx32 sibling
-// plan both kernels are launched; the probe's verdict (XhkWindow::fx_mode, read on the device) makes exactly one
-// of them do the work, so the zero-fill has to suit either.
-int enqueue(Ctx* c, const Prep& pr, Plan& pl, Plan* sib = nullptr) {
+// ---- probe verdicts ---------------------------------------------------------------------------------------------
+bool verdict_matches(const Verdict& v, const PrepEntry& pe, const xh_desc* d, int tile_rows, long long tile_n, int budget, int budget32) {
+  if (!v.used || v.prep_id != pe.id || v.K != d->n_vars || v.dtype != d->dtype || v.w_dtype != d->w_dtype || v.M != d->n_rows || v.N != d->n_cols ||
+      v.w != d->weights || v.wstride != d->w_row_stride || v.tile_rows != tile_rows || v.tile_n != tile_n || v.budget != budget || v.budget32 != budget32 ||
+      v.flags != (d->flags & (XH_FLAG_FORCE_GLOBAL | XH_FLAG_FORCE_WINDOW | XH_FLAG_NO_FX32 | XH_FLAG_NO_ZERO)))
+    return false;
+  for (int k = 0; k < d->n_vars; ++k) if (v.data[k] != d->data[k] || v.stride[k] != d->row_stride[k]) return false;
+  return true;
+}
+
+// Slot of the verdict for this block (existing or newly claimed).  *ready: the host knows the verdict (no probe needed).
+int find_verdict(Ctx* c, const PrepEntry& pe, const xh_desc* d, int tile_rows, long long tile_n, int budget, int budget32, bool* ready) {
+  *ready = false;
+  for (int i = 0; i < kVerdictSlots; ++i) {
+    Verdict& v = c->verdicts[i];
+    if (!verdict_matches(v, pe, d, tile_rows, tile_n, budget, budget32)) continue;
+    v.stamp = ++c->stamp;
+    if (v.state == 1 && cudaEventQuery(c->vev[i]) == cudaSuccess) v.state = 2;
+    if (v.state == 2 && v.stats_pending && cudaEventQuery(c->vev[i]) == cudaSuccess) {
+      // self-check: fraction of the samples since the last check that left the fast path
+      v.stats_pending = false;
+      const unsigned long long cur = verdict_stats_host(c, i);
+      if (v.samples_since > 0) {
+        const double frac = static_cast<double>(cur - v.last_slow) / static_cast<double>(v.samples_since);
+        if (v.base_frac < 0.0) v.base_frac = frac;
+        else if (frac > 2.0 * v.base_frac + 0.02) { v.state = 0; v.base_frac = -1.0; }      // the data changed under the verdict: probe again
+        v.last_slow = cur; v.samples_since = 0;
+      }
+    }
+    *ready = v.state == 2;
+    return i;
+  }
+  int pick = -1;
+  for (int i = 0; i < kVerdictSlots; ++i) if (!c->verdicts[i].used) { pick = i; break; }
+  if (pick < 0) {
+    for (int i = 0; i < kVerdictSlots; ++i)
+      if (c->verdicts[i].state != 1 && (pick < 0 || c->verdicts[i].stamp < c->verdicts[pick].stamp)) pick = i;
+    if (pick < 0) pick = 0;
+  }
+  Verdict& v = c->verdicts[pick];
+  v = Verdict();
+  v.used = true; v.prep_id = pe.id; v.stamp = ++c->stamp;
+  v.K = d->n_vars; v.dtype = d->dtype; v.w_dtype = d->w_dtype; v.M = d->n_rows; v.N = d->n_cols; v.w = d->weights; v.wstride = d->w_row_stride;
+  v.tile_rows = tile_rows; v.tile_n = tile_n; v.budget = budget; v.budget32 = budget32;
+  v.flags = d->flags & (XH_FLAG_FORCE_GLOBAL | XH_FLAG_FORCE_WINDOW | XH_FLAG_NO_FX32 | XH_FLAG_NO_ZERO);
+  for (int k = 0; k < d->n_vars; ++k) { v.data[k] = d->data[k]; v.stride[k] = d->row_stride[k]; }
+  return pick;
+}
+
+// Enqueue zero-fill, window selection and the histogram kernel(s) of one planned block.  `sib` is the k_hist<W = 3>
+// plan of an fp32-weighted block (4 bytes per shared bin).  On a probing call both kernels are launched and the
+// probe's verdict (XhkWindow::fx_mode, read on the device) makes exactly one of them do the work; with a cached
+// verdict the host launches only that one.  `cache` = false (host pipeline: every staged chunk is new data in the same
+// staging buffers) probes every block.
+int enqueue(Ctx* c, const PrepEntry& pe, const xh_desc* d, Plan& pl, Plan* sib, bool cache, int tile_rows, long long tile_n) {
   cudaStream_t s = pl.l.stream;
   const size_t osz = 8;
-  if (sib) {
+  const long long total = pl.p.M * pl.p.N;
+  bool ready = false;
+  int slot = -1;
+  if (pl.need_window) {
+    if (cache) {
+      slot = find_verdict(c, pe, d, tile_rows, tile_n, pl.window_budget, sib ? sib->window_budget : 0, &ready);
+      pl.p.window = verdict_dev(c, slot); pl.p.stats = verdict_stats_dev(c, slot);
+      if (sib) { sib->p.window = pl.p.window; sib->p.stats = pl.p.stats; }
+    } else {
+      pl.p.window = c->window;
+      if (sib) sib->p.window = c->window;
+    }
+  }
+  Plan* run_main = &pl; Plan* run_sib = sib;
+  if (ready && sib) {                       // the host knows which form the probe chose
+    if (verdict_host(c, slot)->fx_mode == 32) { run_main = nullptr; }
+    else { run_sib = nullptr; }
+  }
+  if (run_main && run_sib) {
     pl.p.fx32_sibling = 1;
     const bool same = sib->zero == pl.zero &&
                       (pl.zero != Plan::ZERO_SHARED || (sib->l.grid == pl.l.grid && sib->p.per_cta == pl.p.per_cta));
     if (!same) pl.zero = Plan::ZERO_ALL;
+  } else if (run_main) {
+    pl.p.fx32_sibling = 0;
   }
-  if (pl.zero == Plan::ZERO_ALL) CU(cudaMemsetAsync(pl.p.out, 0, static_cast<size_t>(pl.p.M) * pl.p.B * osz, s));
-  else if (pl.zero == Plan::ZERO_SHARED) CU(xhk_launch_zero_shared_rows(pl.p, pl.l));
-  if (pl.need_window && !pr.window_done) {
-    const long long total = pl.p.M * pl.p.N;
+  Plan& z = run_main ? pl : *sib;
+  if (z.zero == Plan::ZERO_ALL) CU(cudaMemsetAsync(z.p.out, 0, static_cast<size_t>(z.p.M) * z.p.B * osz, s));
+  else if (z.zero == Plan::ZERO_SHARED) CU(xhk_launch_zero_shared_rows(z.p, z.l));
+  if (pl.need_window && !ready) {
+    if (slot >= 0) {     // a fresh (or dropped) verdict: its slow-path counter starts from zero
+      CU(cudaMemsetAsync(verdict_stats_dev(c, slot), 0, 8, s));
+      *reinterpret_cast<volatile unsigned long long*>(c->vslab_host + static_cast<size_t>(slot) * kVerdictSlotBytes + kVerdictStatsOff) = 0ull;
+      Verdict& v = c->verdicts[slot];
+      v.last_slow = 0; v.samples_since = 0; v.calls = 0; v.stats_pending = false; v.base_frac = -1.0;
+    }
     const int n_probe = static_cast<int>(std::min<long long>(total, 1 << 13));
-    CU(xhk_launch_window(pl.p, pl.l, c->window, pl.window_budget, sib ? sib->window_budget : 0, n_probe));
-    pr.window_done = true;
+    CU(xhk_launch_window(pl.p, pl.l, const_cast<XhkWindow*>(pl.p.window), pl.window_budget, sib ? sib->window_budget : 0, n_probe));
+    if (slot >= 0) {
+      CU(cudaMemcpyAsync(c->vslab_host + static_cast<size_t>(slot) * kVerdictSlotBytes, pl.p.window, sizeof(XhkWindow), cudaMemcpyDeviceToHost, s));
+      CU(cudaEventRecord(c->vev[slot], s));
+      c->verdicts[slot].state = 1;
+    }
   }
-  if (sib) CU(xhk_launch_hist(sib->p, sib->l));
-  CU(xhk_launch_hist(pl.p, pl.l));
+  if (run_sib) CU(xhk_launch_hist(run_sib->p, run_sib->l));
+  if (run_main) CU(xhk_launch_hist(pl.p, pl.l));
+  if (slot >= 0) {
+    Verdict& v = c->verdicts[slot];
+    v.samples_since += total;
+    ++v.calls;
+    // look at the slow-path counter after calls 1, 2, 4, 8, 16 and every 16th from then on
+    if (ready && !v.stats_pending && ((v.calls & (v.calls - 1)) == 0 || (v.calls & 15) == 0)) {
+      CU(cudaMemcpyAsync(c->vslab_host + static_cast<size_t>(slot) * kVerdictSlotBytes + kVerdictStatsOff, verdict_stats_dev(c, slot), 8, cudaMemcpyDeviceToHost, s));
+      CU(cudaEventRecord(c->vev[slot], s));
+      v.stats_pending = true;
+    }
+  }
   return XH_OK;
 }
 
-// Plan a block and, for fp32 weights, its fx32 sibling; enqueue both.
-int plan_and_enqueue(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, int tile_rows = 1, long long tile_n = 0) {
+// Plan a block and, for fp32 weights, its fx32 sibling; enqueue.
+int plan_and_enqueue(Ctx* c, const PrepEntry& pe, const xh_desc* d, cudaStream_t stream, bool cache, int tile_rows = 1, long long tile_n = 0) {
+  const Prep& pr = pe.pr;
   Plan pl;
   int rc = plan_block(c, pr, d, stream, pl, tile_rows, tile_n);
   if (rc) return rc;
@@ -462,7 +666,7 @@ int plan_and_enqueue(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stre
     have_sib = sib.p.hist_mode != XHK_GLOBAL && sib.need_window;
     sib.p.store_owned_rows = 0;
   }
-  return enqueue(c, pr, pl, have_sib ? &sib : nullptr);
+  return enqueue(c, pe, d, pl, have_sib ? &sib : nullptr, cache, tile_rows, tile_n);
 }
 
 int validate(const xh_desc* d) {
@@ -482,6 +686,8 @@ int validate(const xh_desc* d) {
   }
   if (d->weights && reinterpret_cast<uintptr_t>(d->weights) % dsize(d->w_dtype)) return fail(XH_ERR_INVALID, "weights not element-aligned");
   if ((d->flags & XH_FLAG_NO_ZERO) && d->out_mem != XH_DEVICE) return fail(XH_ERR_INVALID, "XH_FLAG_NO_ZERO needs a device out");
+  if ((d->flags & XH_FLAG_ASYNC) && (d->mem != XH_DEVICE || d->out_mem != XH_DEVICE || d->kernel_ms))
+    return fail(XH_ERR_INVALID, "XH_FLAG_ASYNC needs device data, a device out and no kernel_ms");
   if (d->n_inner > 1 && (d->n_rows % d->n_inner) != 0) return fail(XH_ERR_INVALID, "column layout: n_rows must be a multiple of n_inner");
   if (d->n_inner < 0) return fail(XH_ERR_INVALID, "negative n_inner");
   if (d->flags & XH_FLAG_DENSITY) {
@@ -520,7 +726,8 @@ int choose_tile_rows(Ctx* c, const Prep& pr, const xh_desc* d) {
   return R >= 2 ? static_cast<int>(R) : 1;
 }
 
-int run_device_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream) {
+int run_device_block(Ctx* c, const PrepEntry& pe, const xh_desc* d, cudaStream_t stream, bool cache) {
+  const Prep& pr = pe.pr;
   const int R = choose_tile_rows(c, pr, d);
   if (R > 1) {
     const long long M = d->n_rows, N = d->n_cols, tiles = M / R, rem = M % R;
@@ -529,20 +736,20 @@ int run_device_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stre
     t.n_rows = tiles; t.n_cols = static_cast<long long>(R) * N;
     for (int k = 0; k < d->n_vars; ++k) t.row_stride[k] = t.n_cols;
     if (d->weights) t.w_row_stride = t.n_cols;
-    int rc = plan_and_enqueue(c, pr, &t, stream, R, N);
+    int rc = plan_and_enqueue(c, pe, &t, stream, cache, R, N);
     if (rc || rem == 0) return rc;
     xh_desc r = *d;                                  // the last M % R rows
     r.n_rows = rem;
     for (int k = 0; k < d->n_vars; ++k) r.data[k] = static_cast<const unsigned char*>(d->data[k]) + static_cast<size_t>(tiles) * R * N * tsz;
     if (d->weights) r.weights = static_cast<const unsigned char*>(d->weights) + static_cast<size_t>(tiles) * R * N * wsz;
     r.out = static_cast<unsigned char*>(d->out) + static_cast<size_t>(tiles) * R * pr.base.B * 8;
-    return run_device_block(c, pr, &r, stream);
+    return run_device_block(c, pe, &r, stream, cache);
   }
-  return plan_and_enqueue(c, pr, d, stream);
+  return plan_and_enqueue(c, pe, d, stream, cache);
 }
 
 // host inputs: double-buffered H2D pipeline feeding device blocks that accumulate into dev_out
-int run_host_pipeline(Ctx* c, const Prep& pr, const xh_desc* d, void* dev_out) {
+int run_host_pipeline(Ctx* c, const PrepEntry& pe, const xh_desc* d, void* dev_out) {
   const int K = d->n_vars;
   const size_t tsz = dsize(d->dtype), wsz = dsize(d->w_dtype);
   const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
@@ -602,7 +809,7 @@ int run_host_pipeline(Ctx* c, const Prep& pr, const xh_desc* d, void* dev_out) {
     }
     CU(cudaEventRecord(c->copied[slot], c->copy_stream));
     CU(cudaStreamWaitEvent(c->stream, c->copied[slot], 0));
-    int rc2 = run_device_block(c, pr, &b, c->stream);
+    int rc2 = run_device_block(c, pe, &b, c->stream, false);   // new data in the same staging slots: probe every chunk
     if (rc2) return rc2;
     CU(cudaEventRecord(c->consumed[slot], c->stream));
     return XH_OK;
@@ -640,8 +847,9 @@ int run_cols_device(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t strea
   XhkParams p = pr.base;
   p.M = d->n_rows; p.N = d->n_cols;
   for (int k = 0; k < d->n_vars; ++k) p.data[k] = d->data[k];
-  p.w = d->weights; p.out = d->out; p.edges = c->edges; p.w_dtype = d->w_dtype;
-  p.lut = reinterpret_cast<const unsigned short*>(static_cast<const unsigned char*>(c->edges) + pr.lut_dev_off);
+  p.w = d->weights; p.out = d->out; p.edges = pr.dev_edges; p.w_dtype = d->w_dtype;
+  p.lut = reinterpret_cast<const unsigned short*>(static_cast<const unsigned char*>(pr.dev_edges) + pr.lut_dev_off);
+  p.stats = c->dummy_stats;
   const long long inner = d->n_inner, outer = d->n_rows / inner;
   const long long tiles = ((inner + tm - 1) / tm) * outer;
   int nsplit = 1;
@@ -693,6 +901,97 @@ int run_cols_host_pipeline(Ctx* c, const Prep& pr, const xh_desc* d, void* dev_o
   return XH_OK;
 }
 
+int allreduce_in_place(Ctx* c, void* buf, size_t count, bool f64, cudaStream_t s) {
+  NC(g_nccl.AllReduce(buf, buf, count, f64 ? kNcclFloat64 : kNcclInt64, kNcclSum, c->comm, s));
+  return XH_OK;
+}
+
+// ---- peer-memory reduction -------------------------------------------------------------------------------------
+constexpr size_t kPeerMaxBytes = 16u << 20;     // larger partials are bandwidth-bound: NCCL's ring / NVLS does those
+
+void peer_release(Ctx* c) {
+  Ctx::Peer& pc = c->peer;
+  for (int r = 0; r < XHK_MAX_PEERS; ++r) { if (pc.mapped[r] && pc.mapped[r] != pc.local) cudaIpcCloseMemHandle(pc.mapped[r]); pc.mapped[r] = nullptr; }
+  if (pc.local) cudaFree(pc.local);
+  pc.local = nullptr; pc.cap = 0; pc.seq = 0;
+}
+
+// Collective over the ranks of c->comm: (re)create the symmetric buffers with `bytes` per slot and map every peer's.
+// Every rank takes the same decisions (same `bytes`, agreement on success through an all-reduce), so either all ranks
+// end up with state 1 or all with state -1.
+int peer_setup(Ctx* c, size_t bytes, cudaStream_t s) {
+  Ctx::Peer& pc = c->peer;
+  const int n = c->comm_ranks;
+  int ok = (n >= 2 && n <= XHK_MAX_PEERS && !std::getenv("XH_NO_P2P")) ? 1 : 0;
+  CU(cudaStreamSynchronize(s));
+  int* dflag = nullptr; unsigned char* dh = nullptr;
+  CU(cudaMalloc(&dflag, sizeof(int)));
+  CU(cudaMalloc(&dh, static_cast<size_t>(XHK_MAX_PEERS + 1) * sizeof(cudaIpcMemHandle_t)));
+  auto agree = [&](int mine, int* all) -> int {       // min over ranks (also a barrier: nobody still reads the old buffers)
+    CU(cudaMemcpyAsync(dflag, &mine, sizeof(int), cudaMemcpyHostToDevice, s));
+    NC(g_nccl.AllReduce(dflag, dflag, 1, kNcclInt32, kNcclMin, c->comm, s));
+    CU(cudaMemcpyAsync(all, dflag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return XH_OK;
+  };
+  int all = 0;
+  int rc = agree(ok, &all);
+  if (rc == XH_OK && all) {
+    peer_release(c);
+    const size_t cap = std::max<size_t>((bytes * 2 + 4095) & ~static_cast<size_t>(4095), 1u << 20);
+    const size_t total = XHK_PEER_FLAG_BYTES + 2 * cap;
+    cudaIpcMemHandle_t mine_h; std::memset(&mine_h, 0, sizeof mine_h);
+    ok = cudaMalloc(&pc.local, total) == cudaSuccess && cudaMemset(pc.local, 0, total) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine_h, pc.local) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    std::vector<cudaIpcMemHandle_t> hs(n);
+    CU(cudaMemcpyAsync(dh, &mine_h, sizeof mine_h, cudaMemcpyHostToDevice, s));
+    NC(g_nccl.AllGather(dh, dh + sizeof(cudaIpcMemHandle_t), sizeof(cudaIpcMemHandle_t), kNcclInt8, c->comm, s));
+    CU(cudaMemcpyAsync(hs.data(), dh + sizeof(cudaIpcMemHandle_t), n * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    rc = agree(ok, &all);                               // every rank has a buffer and a handle?
+    if (rc == XH_OK && all) {
+      for (int r = 0; r < n && ok; ++r) {
+        if (r == c->comm_rank) { pc.mapped[r] = pc.local; continue; }
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, hs[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        pc.mapped[r] = static_cast<unsigned char*>(q);
+      }
+      rc = agree(ok, &all);
+      if (rc == XH_OK && all) pc.cap = cap;
+    }
+  }
+  cudaFree(dflag); cudaFree(dh);
+  if (rc) return rc;
+  if (!all) { peer_release(c); pc.state = -1; } else pc.state = 1;
+  return XH_OK;
+}
+
+// Where the histogram kernels of an XH_FLAG_ALLREDUCE call should write their partial: this rank's slot of the
+// symmetric buffer when the peer path serves the call, else nullptr (NCCL reduces dev_out in place).
+int peer_slot_for_call(Ctx* c, size_t bytes, cudaStream_t s, void** slot) {
+  *slot = nullptr;
+  Ctx::Peer& pc = c->peer;
+  if (c->comm_ranks < 2 || bytes > kPeerMaxBytes || pc.state < 0) return XH_OK;
+  if (pc.state == 0 || bytes > pc.cap) { int rc = peer_setup(c, bytes, s); if (rc) return rc; }
+  if (pc.state != 1) return XH_OK;
+  *slot = pc.local + XHK_PEER_FLAG_BYTES + ((pc.seq + 1) & 1) * pc.cap;
+  return XH_OK;
+}
+
+int peer_allreduce(Ctx* c, size_t count, bool f64, void* out, cudaStream_t s) {
+  Ctx::Peer& pc = c->peer;
+  ++pc.seq;
+  XhkPeerArgs a = {};
+  a.n = c->comm_ranks; a.rank = c->comm_rank; a.seq = pc.seq; a.count = static_cast<long long>(count); a.out = out;
+  for (int r = 0; r < a.n; ++r) {
+    a.flags[r] = reinterpret_cast<unsigned long long*>(pc.mapped[r]);
+    a.slot[r] = pc.mapped[r] + XHK_PEER_FLAG_BYTES + (pc.seq & 1) * pc.cap;
+  }
+  CU(xhk_launch_peer_allreduce(a, f64 ? 1 : 0, s));
+  return XH_OK;
+}
+
 int hist_locked(Ctx* c, const xh_desc* d) {
   CU(cudaSetDevice(c->device));
   const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
@@ -707,69 +1006,87 @@ int hist_locked(Ctx* c, const xh_desc* d) {
     }
     dev_out = c->outbuf;
   }
-  Prep pr;
-  int rc = prep_call(d, pr);
+  PrepEntry* pe = nullptr;
+  int rc = lookup_prep(c, d, &pe);
   if (rc) return rc;
+  const Prep& pr = pe->pr;
+  phase_mark(0);
   cudaStream_t s = (d->mem == XH_DEVICE && d->stream) ? static_cast<cudaStream_t>(d->stream) : c->stream;
+  const bool async = (d->flags & XH_FLAG_ASYNC) != 0;
+  void* final_out = dev_out;         // where the (reduced) histogram ends up; dev_out is where the kernels of this rank write
+  bool via_peers = false;
+  if ((d->flags & XH_FLAG_ALLREDUCE) && out_bytes) {
+    if (!c->comm) return fail(XH_ERR_NCCL, "XH_FLAG_ALLREDUCE: no communicator on device %d (call xh_comm_init_rank first)", c->device);
+    void* slot = nullptr;
+    rc = peer_slot_for_call(c, out_bytes, s, &slot);
+    if (rc) return rc;
+    if (slot) { dev_out = slot; via_peers = true; }
+  }
   if (d->kernel_ms) cudaEventRecord(c->ev0, s);
   if (M == 0 || N == 0 || out_bytes == 0) {
     if (out_bytes && !(d->flags & XH_FLAG_NO_ZERO)) { cudaError_t e = cudaMemsetAsync(dev_out, 0, out_bytes, s); if (e != cudaSuccess) rc = fail(XH_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); }
-  } else {
-    rc = upload_edges(c, pr, s);
-    if (rc == XH_OK) {
-      if (d->n_inner > 1) {
-        if (d->mem == XH_DEVICE) {
-          xh_desc b = *d; b.out = dev_out; b.out_mem = XH_DEVICE;
-          rc = run_cols_device(c, pr, &b, s, (d->flags & XH_FLAG_NO_ZERO) != 0);
-        } else {
-          rc = run_cols_host_pipeline(c, pr, d, dev_out);
-        }
-      } else if (d->mem == XH_DEVICE) {
-        xh_desc b = *d; b.out = dev_out; b.out_mem = XH_DEVICE;
-        rc = run_device_block(c, pr, &b, s);
-      } else {
-        rc = run_host_pipeline(c, pr, d, dev_out);
-      }
+  } else if (d->n_inner > 1) {
+    if (d->mem == XH_DEVICE) {
+      xh_desc b = *d; b.out = dev_out; b.out_mem = XH_DEVICE;
+      rc = run_cols_device(c, pr, &b, s, (d->flags & XH_FLAG_NO_ZERO) != 0);
+    } else {
+      rc = run_cols_host_pipeline(c, pr, d, dev_out);
     }
+  } else if (d->mem == XH_DEVICE) {
+    xh_desc b = *d; b.out = dev_out; b.out_mem = XH_DEVICE;
+    rc = run_device_block(c, *pe, &b, s, true);
+  } else {
+    rc = run_host_pipeline(c, *pe, d, dev_out);
   }
   if (rc == XH_OK && (d->flags & XH_FLAG_ALLREDUCE) && out_bytes) {
-    // partial histograms of the ranks -> global histogram, in place, on the same stream (no host round trip)
-    if (!c->comm) return fail(XH_ERR_NCCL, "XH_FLAG_ALLREDUCE: no communicator on device %d (call xh_comm_init_rank first)", c->device);
-    NC(g_nccl.AllReduce(dev_out, dev_out, static_cast<size_t>(M * B), d->w_dtype == XH_NONE ? kNcclInt64 : kNcclFloat64, kNcclSum, c->comm, s));
+    // partial histograms of the ranks -> global histogram on the same stream (no host round trip): one peer-memory
+    // kernel for small histograms, ncclAllReduce in place otherwise
+    if (via_peers) rc = peer_allreduce(c, static_cast<size_t>(M * B), d->w_dtype != XH_NONE, final_out, s);
+    else rc = allreduce_in_place(c, dev_out, static_cast<size_t>(M * B), d->w_dtype != XH_NONE, s);
+    dev_out = final_out;
   }
-  std::vector<double> wh;               // (stays alive until the stream is synchronised below)
   if (rc == XH_OK && (d->flags & XH_FLAG_DENSITY) && out_bytes) {
     // core.py:444-462 on the device, in place: counts / bin areas / row sums
     int nb[XH_MAX_VARS], f32[XH_MAX_VARS];
-    for (int k = 0; k < d->n_vars; ++k) {
-      nb[k] = d->n_edges[k] - 1; f32[k] = d->widths_f32[k];
-      wh.insert(wh.end(), d->widths[k], d->widths[k] + nb[k]);
-    }
-    if (wh.size() > c->widths_cap) {
-      if (c->widths) cudaFree(c->widths);
-      c->widths = nullptr; c->widths_cap = 0;
-      const size_t cap = std::max<size_t>(wh.size(), 4096);
-      CU(cudaMalloc(&c->widths, cap * sizeof(double)));
-      c->widths_cap = cap;
+    size_t nw = 0;
+    for (int k = 0; k < d->n_vars; ++k) { nb[k] = d->n_edges[k] - 1; f32[k] = d->widths_f32[k]; nw += nb[k]; }
+    bool same = pe->widths.size() == nw && pe->dev_widths;
+    size_t o = 0;
+    for (int k = 0; k < d->n_vars && same; ++k) { same = std::memcmp(pe->widths.data() + o, d->widths[k], sizeof(double) * nb[k]) == 0; o += nb[k]; }
+    if (!same) {       // first density call with these edges (or other widths): upload, blocking
+      pe->widths.clear();
+      for (int k = 0; k < d->n_vars; ++k) pe->widths.insert(pe->widths.end(), d->widths[k], d->widths[k] + nb[k]);
+      if (nw > pe->dev_widths_cap) {
+        if (pe->dev_widths) { cudaDeviceSynchronize(); cudaFree(pe->dev_widths); }
+        pe->dev_widths = nullptr; pe->dev_widths_cap = 0;
+        CU(cudaMalloc(&pe->dev_widths, std::max<size_t>(nw, 64) * sizeof(double)));
+        pe->dev_widths_cap = std::max<size_t>(nw, 64);
+      }
+      CU(cudaStreamSynchronize(s));    // an earlier asynchronous call may still read the old widths
+      CU(cudaMemcpy(pe->dev_widths, pe->widths.data(), nw * sizeof(double), cudaMemcpyHostToDevice));
     }
     if (B > 1024 && static_cast<size_t>(M) > c->rowsums_cap) {
-      if (c->rowsums) cudaFree(c->rowsums);
+      if (c->rowsums) { cudaDeviceSynchronize(); cudaFree(c->rowsums); }
       c->rowsums = nullptr; c->rowsums_cap = 0;
       const size_t cap = std::max<size_t>(static_cast<size_t>(M), 4096);
       CU(cudaMalloc(&c->rowsums, cap * 8));
       c->rowsums_cap = cap;
     }
-    CU(cudaMemcpyAsync(c->widths, wh.data(), wh.size() * sizeof(double), cudaMemcpyHostToDevice, s));
-    CU(xhk_launch_density(dev_out, M, B, d->w_dtype == XH_NONE ? 1 : 0, c->widths, nb, f32, d->n_vars, c->rowsums, s));
+    CU(xhk_launch_density(dev_out, M, B, d->w_dtype == XH_NONE ? 1 : 0, pe->dev_widths, nb, f32, d->n_vars, c->rowsums, s));
   }
   if (rc == XH_OK && d->kernel_ms) cudaEventRecord(c->ev1, s);
   if (rc == XH_OK && d->out_mem == XH_HOST && out_bytes) {
     cudaError_t e = cudaMemcpyAsync(d->out, dev_out, out_bytes, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) rc = fail(XH_ERR_CUDA, "D2H of the histogram failed: %s", cudaGetErrorString(e));
   }
+  phase_mark(1);
+  if (async && rc == XH_OK) return XH_OK;       // device in, device out: the result is valid in stream order
   cudaError_t e = cudaStreamSynchronize(s);
+  phase_mark(2);
   if (rc == XH_OK && e != cudaSuccess) rc = fail(XH_ERR_CUDA, "histogram kernel failed: %s", cudaGetErrorString(e));
   if (d->mem == XH_HOST) { e = cudaStreamSynchronize(c->copy_stream); if (rc == XH_OK && e != cudaSuccess) rc = fail(XH_ERR_CUDA, "copy stream: %s", cudaGetErrorString(e)); }
+  // the stream is idle: every pending probe verdict of this context has reached its host mirror
+  for (int i = 0; i < kVerdictSlots; ++i) if (c->verdicts[i].used && c->verdicts[i].state == 1 && cudaEventQuery(c->vev[i]) == cudaSuccess) c->verdicts[i].state = 2;
   if (rc == XH_OK && d->kernel_ms) { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); *d->kernel_ms = ms; }
   return rc;
 }
@@ -803,9 +1120,15 @@ int xh_shutdown(void) {
     Ctx* c = kv.second;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    peer_release(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->window) cudaFree(c->window);
     if (c->edges) cudaFree(c->edges);
+    for (PrepEntry* e : c->preps) free_prep(e);
+    delete[] c->verdicts;
+    if (c->vslab_dev) cudaFree(c->vslab_dev);
+    if (c->vslab_host) cudaFreeHost(c->vslab_host);
+    for (int i = 0; i < kVerdictSlots; ++i) cudaEventDestroy(c->vev[i]);
     if (c->minmax) cudaFree(c->minmax);
     for (int i = 0; i < 2; ++i) if (c->stage[i]) cudaFree(c->stage[i]);
     if (c->bcast) cudaFree(c->bcast);
@@ -835,12 +1158,21 @@ int xh_device_info(int device, int* sm_count, int* smem_optin_bytes, int64_t* to
 }
 
 int xh_hist(const xh_desc* d) {
+  g_t0 = std::chrono::steady_clock::now();
   int rc = validate(d);
   if (rc) return rc;
   Ctx* c; rc = get_ctx(d->device, &c);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
-  return hist_locked(c, d);
+  rc = hist_locked(c, d);
+  phase_mark(3);
+  return rc;
+}
+
+int xh_last_call_phases(double* us4) {
+  if (!us4) return fail(XH_ERR_INVALID, "null");
+  for (int i = 0; i < 4; ++i) us4[i] = g_phase[i];
+  return XH_OK;
 }
 
 int xh_hist_multi(const xh_desc* d, const int32_t* devices, int32_t n_dev) {
@@ -994,6 +1326,31 @@ int xh_sync(int device) {
   return XH_OK;
 }
 
+int xh_stream_wait(int device, void* producer_stream) {
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  // (cudaStream_t)1 and (cudaStream_t)2 are the legacy and the per-thread default stream handles
+  CU(cudaEventRecord(c->copied[0], static_cast<cudaStream_t>(producer_stream)));
+  CU(cudaStreamWaitEvent(c->stream, c->copied[0], 0));
+  return XH_OK;
+}
+
+int xh_permute(int device, const void* src, void* dst, int elem_size, int ndim, const int64_t* shape, const int32_t* perm) {
+  if (!shape || !perm || ndim < 1 || ndim > XH_MAX_VARS || (elem_size != 4 && elem_size != 8)) return fail(XH_ERR_INVALID, "xh_permute: 1..%d axes of 4- or 8-byte elements", XH_MAX_VARS);
+  long long shp[XH_MAX_VARS]; int prm[XH_MAX_VARS]; unsigned seen = 0; long long total = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] < 0 || perm[i] < 0 || perm[i] >= ndim || (seen >> perm[i] & 1u)) return fail(XH_ERR_INVALID, "xh_permute: bad shape or permutation");
+    seen |= 1u << perm[i]; shp[i] = shape[i]; prm[i] = perm[i]; total *= shape[i];
+  }
+  if (total && (!src || !dst)) return fail(XH_ERR_INVALID, "xh_permute: null buffer");
+  Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  CU(xhk_launch_permute(src, dst, elem_size, ndim, shp, prm, c->stream));   // stream-ordered before any later xh_hist on the library stream
+  return XH_OK;
+}
+
 static int fill_impl(int device, void* ptr, int dtype, int64_t n, uint64_t seed, int64_t offset, int normal) {
   if (!ptr || (dtype != XH_F32 && dtype != XH_F64) || n < 0) return fail(XH_ERR_INVALID, "bad arguments");
   Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
@@ -1043,9 +1400,10 @@ int xh_comm_init_rank(int device, const void* id128, int n_ranks, int rank) {
   Ctx* c; rc = get_ctx(device, &c); if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
-  if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+  if (c->comm) { peer_release(c); c->peer.state = 0; g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
   Id128 id; std::memcpy(id.b, id128, sizeof id.b);
   NC(g_nccl.CommInitRank(&c->comm, n_ranks, id, rank));
+  c->comm_ranks = n_ranks; c->comm_rank = rank; c->peer.state = 0;
   return XH_OK;
 }
 int xh_comm_allreduce(int device, void* dev_buf, int64_t count, int dtype_is_f64) {
@@ -1060,7 +1418,7 @@ int xh_comm_allreduce(int device, void* dev_buf, int64_t count, int dtype_is_f64
 int xh_comm_destroy(int device) {
   Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
-  if (c->comm) { CU(cudaSetDevice(c->device)); NC(g_nccl.CommDestroy(c->comm)); c->comm = nullptr; }
+  if (c->comm) { CU(cudaSetDevice(c->device)); cudaDeviceSynchronize(); peer_release(c); c->peer.state = 0; NC(g_nccl.CommDestroy(c->comm)); c->comm = nullptr; c->comm_ranks = 0; }
   return XH_OK;
 }
 

@@ -17,6 +17,7 @@
 // kernels and the host-callable launchers.
 #include "xhist_kernels.cuh"
 #include <algorithm>
+#include <type_traits>
 
 namespace {
 
@@ -176,6 +177,97 @@ __global__ void __launch_bounds__(256) k_density_scale(void* out, long long M, l
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// device transpose: out = C-contiguous copy of transpose(in, perm).  The reference brings non-trailing reduce axes
+// to the end with np.moveaxis + reshape on the host (core.py:218-226); for device-resident inputs whose layout neither
+// the row nor the column kernel reads in place, this is that copy, done in HBM.
+//   k_permute_tiled : the innermost input axis (a) is not the innermost output axis (b): 32 x 32 tiles through shared
+//                     memory, reads coalesced along a, writes coalesced along b; every other axis is batch
+//   k_permute_rows  : the innermost axis stays innermost: element-wise gather, coalesced on both sides
+// ---------------------------------------------------------------------------------------------
+struct XhkPermute {
+  int nd, da, db;
+  long long shape[XHK_MAX_VARS];        // input shape
+  long long sin[XHK_MAX_VARS];          // input strides (elements)
+  long long sout[XHK_MAX_VARS];         // output stride of INPUT axis i (elements)
+  long long oshape[XHK_MAX_VARS];       // output shape
+  long long osin[XHK_MAX_VARS];         // input stride of OUTPUT axis j
+  long long tiles_a, tiles_b, total;
+};
+
+template <typename E>
+__global__ void __launch_bounds__(256) k_permute_tiled(const E* __restrict__ in, E* __restrict__ out, const __grid_constant__ XhkPermute q) {
+  __shared__ E tile[32][33];
+  long long t = blockIdx.x;
+  const long long ta = t % q.tiles_a; t /= q.tiles_a;
+  const long long tb = t % q.tiles_b; t /= q.tiles_b;
+  long long bin = 0, bout = 0;
+  for (int i = q.nd - 1; i >= 0; --i) {
+    if (i == q.da || i == q.db) continue;
+    const long long c = t % q.shape[i]; t /= q.shape[i];
+    bin += c * q.sin[i]; bout += c * q.sout[i];
+  }
+  const long long a0 = ta * 32, b0 = tb * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8)
+    if (a0 + tx < q.shape[q.da] && b0 + j < q.shape[q.db]) tile[j][tx] = in[bin + (b0 + j) * q.sin[q.db] + (a0 + tx)];
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8)
+    if (b0 + tx < q.shape[q.db] && a0 + j < q.shape[q.da]) out[bout + (a0 + j) * q.sout[q.da] + (b0 + tx)] = tile[tx][j];
+}
+
+template <typename E>
+__global__ void __launch_bounds__(256) k_permute_rows(const E* __restrict__ in, E* __restrict__ out, const __grid_constant__ XhkPermute q) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < q.total; i += stride) {
+    long long r = i, off = 0;
+    for (int j = q.nd - 1; j >= 0; --j) { const long long c = r % q.oshape[j]; r /= q.oshape[j]; off += c * q.osin[j]; }
+    out[i] = in[off];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer-memory all-reduce of partial histograms (the role of dask's .sum over chunk partials, core.py:439, for one rank
+// per GPU on one NVSwitch node).  The partials are small (512 KB for 256 x 256 bins), so the cost of a collective is
+// latency: instead of a ring / tree this is ONE kernel per rank — announce, wait, then read every peer's partial
+// straight over NVLink and add in rank order.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) k_peer_allreduce(const __grid_constant__ XhkPeerArgs a) {
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid < a.n) {
+    __threadfence_system();                       // the partial written by the kernels before this one is visible first
+    st_release_sys(a.flags[tid] + a.rank, a.seq);
+  }
+  if (tid < a.n) {
+    const unsigned long long* mine = a.flags[a.rank] + tid;
+    while (ld_acquire_sys(mine) < a.seq) { }
+  }
+  __syncthreads();
+  const long long n2 = a.count >> 1;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  using V2 = typename std::conditional<std::is_same<T, double>::value, double2, longlong2>::type;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + tid; i < n2; i += stride) {
+    V2 acc = __ldcv(reinterpret_cast<const V2*>(a.slot[0]) + i);
+    for (int r = 1; r < a.n; ++r) { const V2 v = __ldcv(reinterpret_cast<const V2*>(a.slot[r]) + i); acc.x += v.x; acc.y += v.y; }
+    reinterpret_cast<V2*>(a.out)[i] = acc;
+  }
+  if ((a.count & 1) && blockIdx.x == 0 && tid == 0) {
+    T acc = __ldcv(static_cast<const T*>(a.slot[0]) + a.count - 1);
+    for (int r = 1; r < a.n; ++r) acc += __ldcv(static_cast<const T*>(a.slot[r]) + a.count - 1);
+    static_cast<T*>(a.out)[a.count - 1] = acc;
+  }
+}
+
 XhkHistKernel pick(int dtype, int w_dtype, int K, int mode) {
   return dtype == 1 ? xhk_pick_hist_f32(w_dtype, K, mode) : dtype == 2 ? xhk_pick_hist_f64(w_dtype, K, mode) : xhk_pick_hist_i64(w_dtype, K, mode);
 }
@@ -186,13 +278,12 @@ XhkColsKernel pick_cols(int dtype, int w, int K) {
   return dtype == 1 ? xhk_pick_cols_f32(w, K) : dtype == 2 ? xhk_pick_cols_f64(w, K) : xhk_pick_cols_i64(w, K);
 }
 
-// Mode 2 keeps 4 samples x K variables of bins live; with 3+ fp64 variables that spills under the 64-register
-// budget and measured slower than the general kernel (config 5: 4.18 vs 3.93 ms), so it is used for small records only.
+// Mode 2 (branch-free classification for uniform / bounded-step-table variables) handles records above 16 bytes of
+// data per sample two samples at a time (half groups) to stay inside the 64-register budget; see k_hist.
 int kernel_mode(const XhkParams& p, int dtype) {
   if (dtype == 3) return 0;
   if (p.all_uniform) return p.tile_rows > 1 ? 3 : 1;   // row tiling is a compile-time variant of the fast kernel
-  const int rec = p.n_vars * (dtype == 1 ? 4 : 8);
-  return (p.all_branch_free && rec <= 16) ? 2 : 0;
+  return (p.all_branch_free && p.n_vars <= 4) ? 2 : 0;
 }
 
 
@@ -275,6 +366,39 @@ cudaError_t xhk_launch_density(void* out, long long M, long long B, int counts, 
   const int g2 = static_cast<int>(std::min<long long>((M * B + 255) / 256, 148ll * 16));
   if (counts) { k_density_sum<true><<<g1, 256, 0, s>>>(out, B, chunks, sums_dev); k_density_scale<true><<<g2, 256, 0, s>>>(out, M, B, sums_dev, q); }
   else { k_density_sum<false><<<g1, 256, 0, s>>>(out, B, chunks, sums_dev); k_density_scale<false><<<g2, 256, 0, s>>>(out, M, B, sums_dev, q); }
+  return cudaGetLastError();
+}
+
+cudaError_t xhk_launch_peer_allreduce(const XhkPeerArgs& a, int is_f64, cudaStream_t s) {
+  const long long n2 = a.count >> 1;
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((n2 + 511) / 512, 64)));
+  if (is_f64) k_peer_allreduce<double><<<grid, 512, 0, s>>>(a); else k_peer_allreduce<long long><<<grid, 512, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t xhk_launch_permute(const void* in, void* out, int elem_size, int nd, const long long* shape, const int* perm, cudaStream_t s) {
+  if (nd < 1 || nd > XHK_MAX_VARS || (elem_size != 4 && elem_size != 8)) return cudaErrorInvalidValue;
+  XhkPermute q = {};
+  q.nd = nd;
+  long long st = 1, total = 1;
+  for (int i = nd - 1; i >= 0; --i) { q.shape[i] = shape[i]; q.sin[i] = st; st *= shape[i]; total *= shape[i]; }
+  st = 1;
+  for (int j = nd - 1; j >= 0; --j) { q.oshape[j] = shape[perm[j]]; q.osin[j] = q.sin[perm[j]]; q.sout[perm[j]] = st; st *= shape[perm[j]]; }
+  q.total = total;
+  if (total == 0) return cudaSuccess;
+  q.da = nd - 1; q.db = perm[nd - 1];
+  if (q.da == q.db) {
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148ll * 32));
+    if (elem_size == 4) k_permute_rows<uint32_t><<<grid, 256, 0, s>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), q);
+    else k_permute_rows<uint64_t><<<grid, 256, 0, s>>>(static_cast<const uint64_t*>(in), static_cast<uint64_t*>(out), q);
+    return cudaGetLastError();
+  }
+  q.tiles_a = (q.shape[q.da] + 31) / 32; q.tiles_b = (q.shape[q.db] + 31) / 32;
+  long long blocks = q.tiles_a * q.tiles_b;
+  for (int i = 0; i < nd; ++i) if (i != q.da && i != q.db) blocks *= q.shape[i];
+  if (blocks > 2147483647ll) return cudaErrorInvalidValue;
+  if (elem_size == 4) k_permute_tiled<uint32_t><<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), q);
+  else k_permute_tiled<uint64_t><<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const uint64_t*>(in), static_cast<uint64_t*>(out), q);
   return cudaGetLastError();
 }
 

@@ -5,6 +5,8 @@
 #include <stdint.h>
 
 #define XHK_MAX_VARS 8
+#define XHK_MAX_PEERS 16
+#define XHK_PEER_FLAG_BYTES 4096   // head of every rank's symmetric buffer: one u64 arrival flag per peer
 // threads of a k_hist CTA when one CTA owns an SM (register budget: 65536 / XHK_THREADS per thread)
 #ifndef XHK_THREADS
 #define XHK_THREADS 1024
@@ -92,6 +94,8 @@ struct XhkParams {
   int tile_n;                       // samples of one real row
   unsigned tile_magic; int tile_shift;   // q = (umulhi(n, magic) + n) >> shift == n / tile_n for n < 2^31
   int fx_vbits;                     // fixed point: |v| < 2^fx_vbits keeps every per-flush bin sum below 2^63
+  unsigned long long* stats;        // device counter: samples that left the fast path (window spills, weights outside the
+                                    // fixed-point form) — lets the host notice a cached probe verdict that no longer fits
   int fx32_sibling;                 // 1: a k_hist<W = 3> launch of the same block precedes this one and does the work
                                     //    when the probe chose fx_mode 32 (this launch then returns at once)
 };
@@ -128,6 +132,21 @@ cudaError_t xhk_set_smem_limits(int max_optin);
 // (sums_dev: M 8-byte slots of workspace, used when B > 1024)
 cudaError_t xhk_launch_density(void* out, long long M, long long B, int counts, const double* widths_dev, const int* nb, const int* f32,
                                int K, void* sums_dev, cudaStream_t s);
+// Sum of the partial histograms of all ranks through peer memory (NVLink): slot[r] is rank r's partial (count 8-byte
+// items, mapped into this process), flags[r] the head of rank r's symmetric buffer.  Every rank announces `seq` in
+// every peer's flag array, waits until all peers have announced it in its own, then adds the partials in rank order
+// (identical bits on every rank) into `out` (local).  is_f64: float64 sums, else int64.
+struct XhkPeerArgs {
+  const void* slot[XHK_MAX_PEERS];
+  unsigned long long* flags[XHK_MAX_PEERS];
+  int n, rank;
+  unsigned long long seq;
+  long long count;
+  void* out;
+};
+cudaError_t xhk_launch_peer_allreduce(const XhkPeerArgs& a, int is_f64, cudaStream_t s);
+// out = C-contiguous transpose(in, perm) of an nd-dimensional array of 4- or 8-byte elements
+cudaError_t xhk_launch_permute(const void* in, void* out, int elem_size, int nd, const long long* shape, const int* perm, cudaStream_t s);
 cudaError_t xhk_launch_fill(void* ptr, int dtype, long long n, unsigned long long seed, long long offset, int normal, cudaStream_t s);
 cudaError_t xhk_launch_minmax(const void* data, int dtype, long long n, double* out2_dev, cudaStream_t s);
 cudaError_t xhk_launch_flush(void* buf, size_t bytes, cudaStream_t s);

@@ -175,6 +175,20 @@ __device__ __forceinline__ void load4(const double* p, long long g, double (&v)[
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
+// two samples (half a group) per load: big records are classified two samples at a time (see the MODE 2 half-group path)
+__device__ __forceinline__ void load2(const float* p, long long h, float (&v)[2]) {
+  float2 q = __ldcs(reinterpret_cast<const float2*>(p) + h);
+  v[0] = q.x; v[1] = q.y;
+}
+__device__ __forceinline__ void load2(const double* p, long long h, double (&v)[2]) {
+  double2 q = __ldcs(reinterpret_cast<const double2*>(p) + h);
+  v[0] = q.x; v[1] = q.y;
+}
+__device__ __forceinline__ void load2(const long long* p, long long h, long long (&v)[2]) {
+  longlong2 q = __ldcs(reinterpret_cast<const longlong2*>(p) + h);
+  v[0] = q.x; v[1] = q.y;
+}
+
 template <int W> struct WType { using type = float; };   // W = 1 and W = 3: fp32 weights
 template <> struct WType<2> { using type = double; };
 
@@ -199,6 +213,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_wlo[XHK_MAX_VARS], s_wlen[XHK_MAX_VARS];
   __shared__ int s_redo;   // fixed point, row owned by this CTA: a weight did not fit -> redo the segment with float64 adds
+  __shared__ unsigned s_slow;   // samples of this CTA that left the fast path (window spills, weights outside the fixed-point form)
   // fp32 weights are served by two sibling launches; the probe kernel's verdict (XhkWindow::fx_mode) decides which of
   // them does the work, the other one returns at once (no host round trip between probe and histogram):
   //   W == 3 (fx32): 4 bytes per bin — twice the shared window of the 8-byte forms — when (nearly) all weights are
@@ -227,7 +242,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
     }
     s_wlo[tid] = lo; s_wlen[tid] = len;
   }
-  if (tid == 0) s_redo = 0;
+  if (tid == 0) { s_redo = 0; s_slow = 0u; }
   __syncthreads();
   int wlo[KMAX], wlen[KMAX];
   int wtot = (p.hist_mode == XHK_GLOBAL) ? 0 : 1;
@@ -273,6 +288,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   auto global_add = [&](OT* out_row, long long gbin, double wv) {
     if constexpr (W == 0) atomicAdd(out_row + gbin, 1ull); else atomicAdd(out_row + gbin, wv);
   };
+  // an in-range sample that the shared histogram could not take (outside the window, or a weight outside the
+  // fixed-point form): global add + one tick of the CTA's slow-path counter.  The host watches the counter to
+  // notice a cached probe verdict that no longer fits the data (xhist_api.cu, struct Verdict).
+  unsigned nslow = 0;      // MODE 0 / 2 count in a register, the fused fast paths (rare side loops) in shared memory
+  auto note_slow = [&]() { if constexpr (FAST) atomicAdd(&s_slow, 1u); else ++nslow; };
+  auto spill_add = [&](OT* out_row, long long gbin, double wv) { global_add(out_row, gbin, wv); note_slow(); };
   // general path of one sample: exact bins, then shared window / global spill / drop.
   // Returns the window bin when the caller should do the shared add itself, else -1.
   auto general_sample = [&](const T (&x)[KMAX], double wv, OT* out_row, int rowl) -> int {
@@ -292,7 +313,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       long long gbin = 0;
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) if (k < K) gbin = gbin * p.nb[k] + j[k];
-      global_add(out_row, gbin, wv);
+      spill_add(out_row, gbin, wv);
     }
     return -1;
   };
@@ -326,7 +347,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
         const unsigned old = atoms_add_u32(sh_lo + 4u * static_cast<unsigned>(wbin), v);
         if (old + v < old) atomicAdd(out_row + window_to_global(wbin), fx_carry);
       } else {
-        atomicAdd(out_row + window_to_global(wbin), static_cast<double>(w));
+        spill_add(out_row, window_to_global(wbin), static_cast<double>(w));
       }
     } else {
       if (fx) {
@@ -341,7 +362,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
         } else if (owned) {
           s_redo = 1;      // no global add may precede the plain stores of an owned row
         } else {
-          atomicAdd(out_row + window_to_global(wbin), static_cast<double>(w));
+          spill_add(out_row, window_to_global(wbin), static_cast<double>(w));
         }
       } else {
         reds_add_f64(sh_lo + 8u * static_cast<unsigned>(wbin), static_cast<double>(w));
@@ -373,7 +394,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
     }
     if (!ok) return;
     if (inwin) shared_add1(wbin, wsel, out_row);
-    else global_add(out_row, gbin, static_cast<double>(wsel));
+    else spill_add(out_row, gbin, static_cast<double>(wsel));
   };
   auto shared_add4 = [&](const int (&wb)[4], const WT (&wv)[4], OT* out_row) {
 #pragma unroll
@@ -492,6 +513,75 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             load_slot(u, gu + static_cast<long long>(U) * nthr);
           }
         }
+      } else if constexpr (MODE == 2 && (sizeof(T) * KMAX > 16)) {
+        // ---- big records (e.g. three float64 variables + float64 weights = 32 bytes per sample; config 5): the same
+        // branch-free classification as the MODE 2 path below, but over HALF a group (2 samples) at a time, which is
+        // what fits the 64-register budget without spills — the general kernel this replaces for such records spent
+        // its time in divergent search loops (267 instructions per sample, 75 % issue-bound: profiles/r2_ncu_cfg5.md).
+        // Non-uniform variable: table entry of cell c-1 = a bin at or below the sample's, then lut_steps
+        // compare-and-advance steps; window spills leave as inline predicated global REDs.
+        for (long long g = tid; g < 2 * nvec; g += nthr) {          // g counts half groups
+          T xh[KMAX][2]; WT wh[2] = {WT(1), WT(1)};
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) load2(px[k] + head, g, xh[k]);
+          if constexpr (W != 0) load2(pw + head, g, wh);
+          int jb[KMAX][2]; bool okr[2] = {true, true}, cert[2] = {true, true};
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            if (p.uniform[k]) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                cert[e] = cert[e] & uniform_guess<T>(p, k, xh[k][e], jb[k][e]);
+                okr[e] = okr[e] & (static_cast<unsigned>(jb[k][e]) < static_cast<unsigned>(p.nb[k]));
+              }
+            } else {
+              const T lo = Consts<T>::get(p, k, XHK_C_LO), hi = Consts<T>::get(p, k, XHK_C_HI), inv = lut_inv<T>(p, k);
+              const int G = p.lut_n[k], nb = p.nb[k], steps = p.lut_steps[k];
+              const unsigned short* lut = slut + p.lut_off[k];
+              const T* ed = sedges + p.eoff[k];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const T xx = xh[k][e];
+                okr[e] = okr[e] & (xx >= lo) & (xx <= hi);          // NaN: false
+                int c = floor_to_int((xx - lo) * inv);
+                c = max(0, min(c, G - 1));
+                jb[k][e] = static_cast<int>(lut[max(c - 1, 0)]);
+              }
+              for (int st = 0; st < steps; ++st) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int nx = min(jb[k][e] + 1, nb);
+                  jb[k][e] = (ed[nx] <= xh[k][e]) ? nx : jb[k][e];
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 2; ++e) jb[k][e] = min(jb[k][e], nb - 1);   // right-inclusive last bin
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            bool inwin = true; int wbin = local_row(head + 2 * g + e); long long gbin = 0;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              const unsigned jw = static_cast<unsigned>(jb[k][e] - wlo[k]);
+              inwin = inwin & (jw < static_cast<unsigned>(wlen[k]));
+              wbin = wbin * wlen[k] + static_cast<int>(jw);
+              gbin = gbin * p.nb[k] + jb[k][e];
+            }
+            if (cert[e]) {
+              if (okr[e]) {
+                if (inwin) shared_add1(wbin, wh[e], out_row);
+                else { global_add(out_row, gbin, static_cast<double>(wh[e])); ++nslow; }   // in range, outside the shared window
+              }
+            } else {                                   // rare: uncertain sample of a uniform variable -> exact path
+              T x1[KMAX];
+#pragma unroll
+              for (int k = 0; k < KMAX; ++k) x1[k] = xh[k][e];
+              const int wb1 = general_sample(x1, static_cast<double>(wh[e]), out_row, local_row(head + 2 * g + e));
+              if (wb1 >= 0) shared_add1(wb1, wh[e], out_row);
+            }
+          }
+        }
       } else
       for (long long g = tid; g < nvec; g += static_cast<long long>(U) * nthr) {
         T xv[U][KMAX][4];
@@ -566,6 +656,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
               if (good & !inwin) {                      // in range, outside the shared window: one global RED
                 if constexpr (W == 0) atomicAdd(out_row + gbin, 1ull);
                 else atomicAdd(out_row + gbin, static_cast<double>(wv[u][e]));
+                ++nslow;
               }
               unsure |= (live & !cert[e]) ? (1u << (4 * u + e)) : 0u;
             }
@@ -645,7 +736,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
                 for (int e = 0; e < 4; ++e) {
                   if (static_cast<int>(idx[u][e]) >= 0) {
                     const double diff = static_cast<double>(wv[u][e]) - static_cast<double>(vv[e]) * fx_unmul;
-                    if (diff != 0.0) global_add(out_row, window_to_global(static_cast<int>(idx[u][e])), diff);
+                    if (diff != 0.0) spill_add(out_row, window_to_global(static_cast<int>(idx[u][e])), diff);
                   }
                 }
               }
@@ -688,7 +779,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
                 sure = sure & certain & (static_cast<unsigned>(jx) < static_cast<unsigned>(p.nb[k]));
                 gbin = gbin * p.nb[k] + jx;
               }
-              if (sure && !tiled && p.hist_mode != XHK_FULL) global_add(out_row, gbin, static_cast<double>(wsel));
+              if (sure && !tiled && p.hist_mode != XHK_FULL) spill_add(out_row, gbin, static_cast<double>(wsel));
               else {
                 const int wbin = general_sample(x, static_cast<double>(wsel), out_row,
                                                 local_row(head + 4 * (g + static_cast<long long>(sidx >> 2) * nthr) + (sidx & 3)));
@@ -741,7 +832,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
               sure = sure & certain & (static_cast<unsigned>(jx) < static_cast<unsigned>(p.nb[k]));
               gbin = gbin * p.nb[k] + jx;
             }
-            if (sure && !tiled) global_add(out_row, gbin, static_cast<double>(wsel));   // (tiling implies a full window)
+            if (sure && !tiled) spill_add(out_row, gbin, static_cast<double>(wsel));   // (tiling implies a full window)
             else {
               const int wbin = general_sample(x, static_cast<double>(wsel), out_row,
                                               local_row(head + 4 * (g + static_cast<long long>(idx >> 2) * nthr) + (idx & 3)));
@@ -785,7 +876,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             if (rare) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                if (rare & (1u << e)) global_add(out_row, window_to_global(wb[u][e]), static_cast<double>(wv[u][e]));
+                if (rare & (1u << e)) spill_add(out_row, window_to_global(wb[u][e]), static_cast<double>(wv[u][e]));
                 if (rare & (16u << e)) global_add(out_row, window_to_global(wb[u][e]), fx_carry);
               }
             }
@@ -820,7 +911,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             for (int u = 0; u < U; ++u)
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (inexact & (1u << (4 * u + e))) global_add(out_row, window_to_global(wb[u][e]), static_cast<double>(wv[u][e]));
+                if (inexact & (1u << (4 * u + e))) spill_add(out_row, window_to_global(wb[u][e]), static_cast<double>(wv[u][e]));
           }
         } else {
 #pragma unroll
@@ -864,6 +955,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
     fx = fx_launch;     // (a redone segment ran with float64 adds)
     __syncthreads();
   }
+  if constexpr (!FAST) { if (nslow) atomicAdd(&s_slow, nslow); }
+  __syncthreads();
+  if (tid == 0 && s_slow) atomicAdd(p.stats, static_cast<unsigned long long>(s_slow));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -136,12 +136,14 @@ class NcclCommunicator(Communicator):
 
 
 def histogram(*local_args, bins=None, range=None, axis=None, weights=None, density=False, block_size="auto",
-              comm: Communicator = None, sharded_axis=0, gather=False):
+              comm: Communicator = None, sharded_axis=0, gather=False, out=None):
     """SPMD histogram: every rank passes ITS shard of the arrays (split along ``sharded_axis``).
 
     Same arguments as ``core.histogram`` otherwise.  Returns ``(h, edges)``; when the sharded axis
     is reduced ``h`` is the global histogram on every rank, when it is kept ``h`` is this rank's
-    slab (or the assembled array with ``gather=True``).
+    slab (or the assembled array with ``gather=True``).  ``out`` (device-resident shards, reduced sharded axis, NCCL
+    communicator): a ``DeviceArray`` that receives the global histogram — the call only enqueues (kernels, reduction
+    over NVLink, density) and the result stays in HBM, valid in stream order.
     """
     comm = comm or Communicator()
     a0 = local_args[0]
@@ -167,11 +169,15 @@ def histogram(*local_args, bins=None, range=None, axis=None, weights=None, densi
     if sharded_axis in red:
         if isinstance(comm, NcclCommunicator):
             # ONE native call: histogram kernels -> ncclAllReduce of the partials in HBM -> density -> D2H of the result
-            h = _fused_allreduce(local_args, weights, edges, axis, nd, comm, density)
+            h = _fused_allreduce(local_args, weights, edges, axis, nd, comm, density, out)
             return h, edges
+        if out is not None:
+            raise TypeError("out= needs an NcclCommunicator")
         h, _ = _core.histogram(*local_args, bins=edges, axis=axis, weights=weights, density=False, block_size=block_size)
         h = comm.allreduce_sum(np.ascontiguousarray(h))         # partial histograms -> global (core.py:439)
     else:
+        if out is not None:
+            raise TypeError("out= is for a reduced sharded axis")
         h, _ = _core.histogram(*local_args, bins=edges, axis=axis, weights=weights, density=False, block_size=block_size)
         if gather:
             kept = [i for i in _range(nd) if i not in red]
@@ -186,7 +192,7 @@ def histogram(*local_args, bins=None, range=None, axis=None, weights=None, densi
     return h, edges
 
 
-def _fused_allreduce(local_args, weights, edges, axis, nd, comm, density):
+def _fused_allreduce(local_args, weights, edges, axis, nd, comm, density, out=None):
     """Shard (host or device resident) -> partial histogram in HBM -> ncclAllReduce in place -> density on the device
     -> one D2H of the finished result, all inside one ``xh_hist`` call (XH_FLAG_ALLREDUCE [| XH_FLAG_DENSITY])."""
     ax = None if axis is None else [int(a) if a >= 0 else nd + int(a) for a in np.atleast_1d(axis)]
@@ -195,6 +201,12 @@ def _fused_allreduce(local_args, weights, edges, axis, nd, comm, density):
         arrays = list(np.broadcast_arrays(*[np.asarray(a) for a in arrays]))
     on_device = density and all(np.asarray(e).dtype in (np.float32, np.float64) for e in edges)
     widths = [np.diff(e) for e in edges] if on_device else None
+    if out is not None:
+        if not _core.is_device_array(local_args[0]) or (density and not on_device):
+            raise TypeError("out= needs device-resident shards (and float bin edges for density=True)")
+        _core._bincount(*arrays, weights=weights is not None, axis=ax, bins=edges, _flags=_cabi.XH_FLAG_ALLREDUCE | _cabi.XH_FLAG_ASYNC,
+                        _density_widths=widths, _out_device=out.reshape(-1))
+        return out
     h = _core._bincount(*arrays, weights=weights is not None, axis=ax, bins=edges, _flags=_cabi.XH_FLAG_ALLREDUCE,
                         _density_widths=widths, _devices=[comm.device])
     if ax is not None:

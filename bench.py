@@ -443,6 +443,11 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    cpu_sample = None
+    if rank == 0 and not args.no_cpu:      # host copy of the CPU leg's slab (config_rows releases the device arrays)
+        threads = os.cpu_count() or 1
+        m = min(args.samples_cpu or pick_cpu_sample(threads), n)
+        cpu_sample = tuple(a.flat_slice(0, m).to_numpy() for a in (x, y, w))
     configs = None
     if not args.no_configs:
         configs = config_rows(rank, world, dev, comm, peak, x, y, w, n, D, core, DeviceArray, PinnedArray, _cabi, timed_steps, max_over_ranks)
@@ -469,11 +474,10 @@ def main():
                 "peak_source": peak_src}
 
     cpu = None
-    if not args.no_cpu:
+    if cpu_sample is not None:
         threads = os.cpu_count() or 1
-        m = args.samples_cpu or pick_cpu_sample(threads)
-        m = min(m, n)
-        xs, ys, ws = (a.flat_slice(0, m).to_numpy() for a in (x, y, w))
+        xs, ys, ws = cpu_sample
+        m = xs.size
         rate, _ = cpu_throughput(xs, ys, ws, threads)
         rate1, _ = cpu_throughput(xs[: m // 8], ys[: m // 8], ws[: m // 8], 1)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": cpu_impl()[0],
@@ -563,8 +567,9 @@ def multi_rank_parity(rank, world, dev, n, x, y, w, comm, bins, D, core, O, Devi
         a, b, c = host_slab(mm, seeds=(21, 22, 23))
         hm, _ = core.histogram(a, b, bins=bins, weights=c, devices=[0, 1])                              # columns sharded + NCCL
         wm, _ = O.histogram(a, b, bins=bins, weights=c, threads=8)
-        hr, _ = core.histogram(a.reshape(7, -1)[:, :400000], b.reshape(7, -1)[:, :400000], bins=bins, axis=1, devices=[0, 1])   # rows sharded
-        wr, _ = O.histogram(a.reshape(7, -1)[:, :400000], b.reshape(7, -1)[:, :400000], bins=bins, axis=1)
+        a7, b7 = a[:2_800_000].reshape(7, -1), b[:2_800_000].reshape(7, -1)
+        hr, _ = core.histogram(a7, b7, bins=bins, axis=1, devices=[0, 1])                               # rows sharded
+        wr, _ = O.histogram(a7, b7, bins=bins, axis=1)
         out["xh_hist_multi_columns_max_rel_err"] = float(np.max(np.abs(hm - wm)) / np.max(np.abs(wm)))
         out["xh_hist_multi_rows_bit_exact"] = bool(np.array_equal(hr, wr))
         ok = ok and out["xh_hist_multi_columns_max_rel_err"] <= 1e-6 and out["xh_hist_multi_rows_bit_exact"]

@@ -57,6 +57,8 @@ typedef enum xh_mem { XH_HOST = 0, XH_DEVICE = 1 } xh_mem;
                                    role of dask's blockwise + .sum in core.py:429-439                              */
 #define XH_FLAG_ASYNC 128u      /* device data and device out only: return once the work is enqueued on the stream; `out`
                                    is valid in stream order (xh_sync, or any later call on the same stream, orders after it) */
+#define XH_FLAG_OUT_PINNED 256u  /* host `out` is page-locked memory from xh_host_alloc (device-mapped): the library lets the GPU
+                                   write the result into it directly instead of landing it in its own pinned buffer and copying */
 #define XH_FLAG_DENSITY 32u     /* finish the density on the device (core.py:444-462): out becomes float64
                                    counts / bin areas / row sum, also without weights; needs widths[]         */
 
@@ -140,7 +142,7 @@ int xh_minmax(int device, const void* data, int dtype, int mem, int64_t n, doubl
 /* device buffers for the device-resident path ---------------------------------------- */
 int xh_malloc(int device, size_t bytes, void** ptr);
 int xh_free(int device, void* ptr);
-int xh_host_alloc(size_t bytes, void** ptr);            /* pinned host memory for fast H2D */
+int xh_host_alloc(size_t bytes, void** ptr);            /* pinned, device-mapped host memory: fast H2D source, direct result target */
 int xh_host_free(void* ptr);
 int xh_memcpy(int device, void* dst, const void* src, size_t bytes, int dst_mem, int src_mem);
 int xh_memset(int device, void* dst, int value, size_t bytes);

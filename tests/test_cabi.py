@@ -56,7 +56,7 @@ def test_density_flag_needs_widths_and_is_rejected_early():
     out = (C.c_double * 2)()
     d.n_vars, d.dtype, d.n_rows, d.n_cols = 1, _cabi.XH_F32, 1, 4
     d.data[0] = C.cast(x, C.c_void_p); d.row_stride[0] = 4
-    d.edges[0] = C.cast(e, C.POINTER(C.c_double)); d.n_edges[0] = 3
+    d.edges[0] = C.cast(e, C.c_void_p); d.n_edges[0] = 3
     d.out = C.cast(out, C.c_void_p)
     d.flags = _cabi.XH_FLAG_DENSITY                       # no widths[]
     assert _cabi.lib().xh_hist(C.byref(d)) == -1 and "widths" in _cabi.last_error()

@@ -22,6 +22,7 @@ XH_FLAG_NO_FX32 = 16
 XH_FLAG_DENSITY = 32
 XH_FLAG_ALLREDUCE = 64
 XH_FLAG_ASYNC = 128
+XH_FLAG_OUT_PINNED = 256
 XH_NCCL_UNIQUE_ID_BYTES = 128
 
 _ERRORS = {
@@ -52,14 +53,14 @@ class XhDesc(C.Structure):
         ("row_stride", C.c_int64 * XH_MAX_VARS),
         ("weights", C.c_void_p),
         ("w_row_stride", C.c_int64),
-        ("edges", C.POINTER(C.c_double) * XH_MAX_VARS),
+        ("edges", C.c_void_p * XH_MAX_VARS),          # const double* [XH_MAX_VARS]
         ("n_edges", C.c_int32 * XH_MAX_VARS),
         ("out", C.c_void_p),
         ("stream", C.c_void_p),
         ("kernel_ms", C.POINTER(C.c_float)),
-        ("iedges", C.POINTER(C.c_int64) * XH_MAX_VARS),
+        ("iedges", C.c_void_p * XH_MAX_VARS),         # const int64_t* [XH_MAX_VARS]
         ("n_inner", C.c_int64),
-        ("widths", C.POINTER(C.c_double) * XH_MAX_VARS),
+        ("widths", C.c_void_p * XH_MAX_VARS),         # const double* [XH_MAX_VARS]
         ("widths_f32", C.c_int32 * XH_MAX_VARS),
     ]
 
@@ -103,7 +104,8 @@ PROTOTYPES = {
 
 
 def library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+    """In-tree shared library; ``XHIST_B200_LIB`` points at another build of it (A/B measurements of kernel variants)."""
+    return os.environ.get("XHIST_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 def lib():

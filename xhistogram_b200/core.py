@@ -28,7 +28,7 @@ from collections.abc import Iterable
 import numpy as np
 
 from . import _cabi
-from .device import DeviceArray, as_device_view, is_device_array
+from .device import DeviceArray, as_device_view, is_device_array, result_pool
 
 _range = range
 
@@ -173,7 +173,7 @@ def _resolve_edges(a, bins, range_, weights):
     """Bin edges of one variable, identical to ``np.histogram_bin_edges(a, bins, range, weights)``."""
     if isinstance(bins, np.ndarray) and bins.ndim == 1 and bins.size >= 2 and bins.dtype.kind in "fiu":
         # explicit edges: np.histogram_bin_edges returns them as they are after this check (_histograms_impl.py:427-431)
-        if (bins[:-1] > bins[1:]).any():
+        if not _edge_info(bins).monotonic:
             raise ValueError("`bins` must increase monotonically, when an array")
         return bins
     device = is_device_array(a)
@@ -330,7 +330,8 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
     return out.reshape(kept_axes_shape + nbins)
 
 
-def _bincount_device(arrays, w, shape, nd, full, axis, bins, kept_axes_shape, nbins, flags, timing, out_device, density_widths):
+def _bincount_device(arrays, w, shape, nd, full, axis, bins, kept_axes_shape, nbins, flags, timing, out_device, density_widths,
+                     infos=None):
     """Device-resident block.  Reduced axes may be any subset: trailing axes are read in place as rows, one contiguous
     block of leading/middle axes in place as columns (when the bin space fits the column kernel), anything else is
     brought to row layout by a transposing copy ON THE DEVICE (xh_permute) — the reference does the same copy on the
@@ -351,7 +352,7 @@ def _bincount_device(arrays, w, shape, nd, full, axis, bins, kept_axes_shape, nb
 
     def call(ptrs, wptr, M, N, n_inner):
         return _desc_call(ptrs, [N] * len(ptrs), wptr, N if wptr is not None else 0, bins, M, N, xdt, wdt,
-                          _cabi.XH_DEVICE, dev, None, flags, timing, out_device, n_inner, density_widths)
+                          _cabi.XH_DEVICE, dev, None, flags, timing, out_device, n_inner, density_widths, infos)
 
     def finish(out):
         return out if out_device is not None else out.reshape(kept_axes_shape + nbins)   # a DeviceArray stays flat, in HBM
@@ -425,20 +426,55 @@ def _host_call(arrs, strides, wrow, bins, M, N, xdt, devices, flags, timing, den
                       devices[0] if devices else _default_device(), devices, flags, timing, density_widths=density_widths)
 
 
-def _edge_pointer(b, want, ptype, keep):
-    """(pointer to a contiguous ``want``-typed copy of the edges, number of edges).  The copy is kept alive in ``keep``
-    for the duration of the call; edges that already are contiguous ``want`` arrays are passed as they are."""
-    e = b if (isinstance(b, np.ndarray) and b.dtype == want and b.flags.c_contiguous) else np.ascontiguousarray(b, dtype=want)
-    keep.append(e)
-    return C.cast(e.ctypes.data, ptype), e.size
+class _EdgeInfo:
+    """What a call needs from one edge array, computed once per edge CONTENT: a contiguous float64 (or int64) copy with a
+    stable address, its bin widths as numpy's ``np.diff`` holds them, and the address of a float64 copy of those."""
+
+    __slots__ = ("n", "ptr", "iptr", "widths", "wptr", "w_f32", "monotonic", "_keep")
+
+    def __init__(self, b):
+        b = np.asarray(b)
+        self.n = b.size
+        self.monotonic = not bool((b[:-1] > b[1:]).any()) if b.ndim == 1 else True
+        keep = []
+        self.ptr = self.iptr = self.wptr = None
+        self.widths, self.w_f32 = None, 0
+        if b.dtype.kind in "iu" or b.dtype.kind in "mM":
+            ei = np.ascontiguousarray(b.view(np.int64) if b.dtype.kind in "mM" else b, dtype=np.int64)
+            keep.append(ei)
+            self.iptr = ei.__array_interface__["data"][0]
+        if b.dtype.kind in "fiu":
+            ef = np.array(b, dtype=np.float64, order="C")                # private copy: later in-place edits of b cannot reach it
+            keep.append(ef)
+            self.ptr = ef.__array_interface__["data"][0]
+            if b.dtype.kind == "f" and b.size >= 2:
+                self.widths = np.diff(b)
+                wf = np.ascontiguousarray(self.widths, dtype=np.float64)
+                keep.append(wf)
+                self.wptr = wf.__array_interface__["data"][0]
+                self.w_f32 = 1 if self.widths.dtype == np.float32 else 0
+        self._keep = keep
 
 
-_PD = C.POINTER(C.c_double)
-_PI = C.POINTER(C.c_int64)
+_edge_cache = {}
+
+
+def _edge_info(b):
+    """Cached ``_EdgeInfo`` of an edge array, keyed by dtype and raw content (a few KB: hashing it costs about a microsecond,
+    an order of magnitude less than re-deriving pointers and widths through numpy and ctypes on every call)."""
+    if not isinstance(b, np.ndarray):
+        b = np.asarray(b)
+    key = (b.dtype.str, b.tobytes())
+    info = _edge_cache.get(key)
+    if info is None:
+        if len(_edge_cache) >= 64:
+            _edge_cache.pop(next(iter(_edge_cache)))
+        info = _edge_cache[key] = _EdgeInfo(b)
+    return info
 
 
 def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing, out_device=None,
-               n_inner=0, density_widths=None):
+               n_inner=0, density_widths=None, infos=None):
     K = len(arrs)
     if K > _cabi.XH_MAX_VARS:
         raise NotImplementedError(f"at most {_cabi.XH_MAX_VARS} variables are supported")
@@ -454,11 +490,14 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
         else:
             d.data[k] = arrs[k]
         d.row_stride[k] = strides[k]
+        info = infos[k] if infos is not None else _edge_info(bins[k])
+        keep.append(info)
         if dtype == _cabi.XH_I64:
-            d.iedges[k], d.n_edges[k] = _edge_pointer(bins[k], np.int64, _PI, keep)
+            d.iedges[k] = info.iptr
         else:
-            d.edges[k], d.n_edges[k] = _edge_pointer(bins[k], np.float64, _PD, keep)
-        B *= d.n_edges[k] - 1
+            d.edges[k] = info.ptr
+        d.n_edges[k] = info.n
+        B *= info.n - 1
     if w is not None:
         d.weights = (w.ctypes.data if w.size else None) if mem == _cabi.XH_HOST else w
         d.w_row_stride = wstride
@@ -468,8 +507,11 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
         # density on the device: widths as float64 values plus how numpy holds them (float32 products round to float32)
         d.flags |= _cabi.XH_FLAG_DENSITY
         for k in _range(K):
-            d.widths[k], _ = _edge_pointer(density_widths[k], np.float64, _PD, keep)
-            d.widths_f32[k] = 1 if density_widths[k].dtype == np.float32 else 0
+            info = keep[k]
+            if info.wptr is None:
+                raise TypeError("density on the device needs float bin edges")
+            d.widths[k] = info.wptr
+            d.widths_f32[k] = info.w_f32
     if out_device is not None:
         if out_device.size != M * B or out_device.dtype.itemsize != 8:
             raise ValueError("device output buffer has the wrong size")
@@ -478,11 +520,18 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
     else:
         if d.flags & _cabi.XH_FLAG_ASYNC:
             raise ValueError("an asynchronous call needs a device output buffer")
-        out = np.empty((M, B), dtype=np.int64 if (w is None and density_widths is None) else np.float64)
+        odt = np.int64 if (w is None and density_widths is None) else np.float64
         if (M * N == 0 and not (d.flags & _cabi.XH_FLAG_ALLREDUCE)) or M * B == 0:
+            out = np.empty((M, B), dtype=odt)
             out[...] = np.nan if (density_widths is not None and B) else 0      # 0 / area / 0, as numpy computes it
             return out
-        d.out = out.ctypes.data
+        out = result_pool.array((M, B), odt) if (devices is None or len(devices) <= 1) else None
+        if out is not None:
+            d.flags |= _cabi.XH_FLAG_OUT_PINNED            # page-locked, device-mapped: the GPU writes the result in place
+            d.out = out.__array_interface__["data"][0]
+        else:
+            out = np.empty((M, B), dtype=odt)
+            d.out = out.ctypes.data
     ms = None
     if timing is None and _timing_sink is not None and not (d.flags & _cabi.XH_FLAG_ASYNC):
         timing = {}
@@ -537,6 +586,7 @@ def _histogram_device(args, bins, range, axis, weights, density, out):
     bins = _ensure_correctly_formatted_bins(bins, n_inputs)
     range = _ensure_correctly_formatted_range(range, n_inputs)
     bins = [_resolve_edges(a, b, r, None) for a, b, r in zip(args, bins, range)]
+    infos = [_edge_info(b) for b in bins]
     for b in bins:
         if b.dtype.kind not in "fiu":
             raise TypeError(f"unsupported bin-edge dtype {b.dtype} for device-resident data")
@@ -547,10 +597,10 @@ def _histogram_device(args, bins, range, axis, weights, density, out):
     device_density = density and all(b.dtype.kind == "f" and b.dtype.itemsize in (4, 8) for b in bins)
     if density and not device_density and out is not None:
         raise TypeError("density=True with out= needs float bin edges")
-    widths = [np.diff(b) for b in bins] if device_density else None
+    widths = [i.widths for i in infos] if device_density else None
     flags = _cabi.XH_FLAG_ASYNC if out is not None else 0
     h = _bincount_device(list(args), weights, shape, ndim, full, axis, bins, kept_axes_shape, nbins, flags, None,
-                         out.reshape(-1) if out is not None else None, widths)
+                         out.reshape(-1) if out is not None else None, widths, infos)
     if out is not None:
         return out.reshape(kept_shape + nbins), bins
     h = h.reshape(kept_shape + nbins)
@@ -649,7 +699,7 @@ def histogram(*args, bins=None, range=None, axis=None, weights=None, density=Fal
                                    adjust_chunks=adjust_chunks, meta=np.array((), dtype), **bincount_kwargs)
         bin_counts = bin_counts.sum(drop_axes)
     else:
-        widths = [np.diff(b) for b in bins] if device_density else None
+        widths = [_edge_info(b).widths for b in bins] if device_density else None
         bin_counts = _bincount(*all_arrays, _devices=devices, _density_widths=widths, **bincount_kwargs).squeeze(drop_axes)
 
     if device_density:

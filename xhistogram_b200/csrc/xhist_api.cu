@@ -114,6 +114,8 @@ struct Ctx {
   size_t rowsums_cap = 0;
   void* outbuf = nullptr;            // device histogram when the caller's out is host memory
   size_t outbuf_cap = 0;
+  void* outpin = nullptr;            // pinned landing buffer for small results (a D2H straight into pageable memory costs
+  size_t outpin_cap = 0;             // tens of microseconds of driver staging; DMA into pinned memory + memcpy does not)
   void* comm = nullptr;              // NCCL communicator (multi-process mode)
   int comm_ranks = 0, comm_rank = 0;
   // peer-memory reduction of small partial histograms (one rank per GPU, same node): every rank's symmetric buffer
@@ -686,6 +688,7 @@ int validate(const xh_desc* d) {
   }
   if (d->weights && reinterpret_cast<uintptr_t>(d->weights) % dsize(d->w_dtype)) return fail(XH_ERR_INVALID, "weights not element-aligned");
   if ((d->flags & XH_FLAG_NO_ZERO) && d->out_mem != XH_DEVICE) return fail(XH_ERR_INVALID, "XH_FLAG_NO_ZERO needs a device out");
+  if ((d->flags & XH_FLAG_OUT_PINNED) && d->out_mem != XH_HOST) return fail(XH_ERR_INVALID, "XH_FLAG_OUT_PINNED is for a host out");
   if ((d->flags & XH_FLAG_ASYNC) && (d->mem != XH_DEVICE || d->out_mem != XH_DEVICE || d->kernel_ms))
     return fail(XH_ERR_INVALID, "XH_FLAG_ASYNC needs device data, a device out and no kernel_ms");
   if (d->n_inner > 1 && (d->n_rows % d->n_inner) != 0) return fail(XH_ERR_INVALID, "column layout: n_rows must be a multiple of n_inner");
@@ -901,6 +904,19 @@ int run_cols_host_pipeline(Ctx* c, const Prep& pr, const xh_desc* d, void* dev_o
   return XH_OK;
 }
 
+constexpr size_t kPinnedResultMax = 8u << 20;
+
+// pinned, device-mapped landing buffer for small host results
+bool ensure_outpin(Ctx* c, size_t bytes) {
+  if (bytes <= c->outpin_cap) return true;
+  if (c->outpin) { cudaDeviceSynchronize(); cudaFreeHost(c->outpin); }
+  c->outpin = nullptr; c->outpin_cap = 0;
+  const size_t cap = std::max<size_t>(bytes, 1u << 20);
+  if (cudaHostAlloc(&c->outpin, cap, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { c->outpin = nullptr; cudaGetLastError(); return false; }
+  c->outpin_cap = cap;
+  return true;
+}
+
 int allreduce_in_place(Ctx* c, void* buf, size_t count, bool f64, cudaStream_t s) {
   NC(g_nccl.AllReduce(buf, buf, count, f64 ? kNcclFloat64 : kNcclInt64, kNcclSum, c->comm, s));
   return XH_OK;
@@ -1013,6 +1029,7 @@ int hist_locked(Ctx* c, const xh_desc* d) {
   phase_mark(0);
   cudaStream_t s = (d->mem == XH_DEVICE && d->stream) ? static_cast<cudaStream_t>(d->stream) : c->stream;
   const bool async = (d->flags & XH_FLAG_ASYNC) != 0;
+  bool density_landed = false;       // the density kernel wrote the finished result into the pinned landing buffer
   void* final_out = dev_out;         // where the (reduced) histogram ends up; dev_out is where the kernels of this rank write
   bool via_peers = false;
   if ((d->flags & XH_FLAG_ALLREDUCE) && out_bytes) {
@@ -1065,24 +1082,36 @@ int hist_locked(Ctx* c, const xh_desc* d) {
       CU(cudaStreamSynchronize(s));    // an earlier asynchronous call may still read the old widths
       CU(cudaMemcpy(pe->dev_widths, pe->widths.data(), nw * sizeof(double), cudaMemcpyHostToDevice));
     }
-    if (B > 1024 && static_cast<size_t>(M) > c->rowsums_cap) {
-      if (c->rowsums) { cudaDeviceSynchronize(); cudaFree(c->rowsums); }
-      c->rowsums = nullptr; c->rowsums_cap = 0;
-      const size_t cap = std::max<size_t>(static_cast<size_t>(M), 4096);
-      CU(cudaMalloc(&c->rowsums, cap * 8));
-      c->rowsums_cap = cap;
+    // a small result for the host: one launch that writes the finished density straight into the pinned landing buffer
+    void* landing = (d->flags & XH_FLAG_OUT_PINNED) ? d->out : nullptr;      // the caller's own pinned result memory, or ours
+    if (d->out_mem == XH_HOST && out_bytes <= kPinnedResultMax && M <= (1 << 20) && (landing || ensure_outpin(c, out_bytes))) {
+      if (!landing) landing = c->outpin;
+      CU(xhk_launch_density_small(dev_out, static_cast<double*>(landing), M, B, d->w_dtype == XH_NONE ? 1 : 0, pe->dev_widths, nb, f32, d->n_vars, s));
+      density_landed = true;
+    } else {
+      if (B > 1024 && static_cast<size_t>(M) > c->rowsums_cap) {
+        if (c->rowsums) { cudaDeviceSynchronize(); cudaFree(c->rowsums); }
+        c->rowsums = nullptr; c->rowsums_cap = 0;
+        const size_t cap = std::max<size_t>(static_cast<size_t>(M), 4096);
+        CU(cudaMalloc(&c->rowsums, cap * 8));
+        c->rowsums_cap = cap;
+      }
+      CU(xhk_launch_density(dev_out, M, B, d->w_dtype == XH_NONE ? 1 : 0, pe->dev_widths, nb, f32, d->n_vars, c->rowsums, s));
     }
-    CU(xhk_launch_density(dev_out, M, B, d->w_dtype == XH_NONE ? 1 : 0, pe->dev_widths, nb, f32, d->n_vars, c->rowsums, s));
   }
   if (rc == XH_OK && d->kernel_ms) cudaEventRecord(c->ev1, s);
-  if (rc == XH_OK && d->out_mem == XH_HOST && out_bytes) {
-    cudaError_t e = cudaMemcpyAsync(d->out, dev_out, out_bytes, cudaMemcpyDeviceToHost, s);
+  bool via_pin = density_landed && !(d->flags & XH_FLAG_OUT_PINNED);
+  if (rc == XH_OK && d->out_mem == XH_HOST && out_bytes && !density_landed) {
+    void* dst = d->out;
+    if (!(d->flags & XH_FLAG_OUT_PINNED) && out_bytes <= kPinnedResultMax && ensure_outpin(c, out_bytes)) { dst = c->outpin; via_pin = true; }
+    cudaError_t e = cudaMemcpyAsync(dst, dev_out, out_bytes, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) rc = fail(XH_ERR_CUDA, "D2H of the histogram failed: %s", cudaGetErrorString(e));
   }
   phase_mark(1);
   if (async && rc == XH_OK) return XH_OK;       // device in, device out: the result is valid in stream order
   cudaError_t e = cudaStreamSynchronize(s);
   phase_mark(2);
+  if (via_pin && e == cudaSuccess && rc == XH_OK) std::memcpy(d->out, c->outpin, out_bytes);
   if (rc == XH_OK && e != cudaSuccess) rc = fail(XH_ERR_CUDA, "histogram kernel failed: %s", cudaGetErrorString(e));
   if (d->mem == XH_HOST) { e = cudaStreamSynchronize(c->copy_stream); if (rc == XH_OK && e != cudaSuccess) rc = fail(XH_ERR_CUDA, "copy stream: %s", cudaGetErrorString(e)); }
   // the stream is idle: every pending probe verdict of this context has reached its host mirror
@@ -1134,6 +1163,7 @@ int xh_shutdown(void) {
     if (c->bcast) cudaFree(c->bcast);
     if (c->flush) cudaFree(c->flush);
     if (c->outbuf) cudaFree(c->outbuf);
+    if (c->outpin) cudaFreeHost(c->outpin);
     if (c->widths) cudaFree(c->widths);
     if (c->rowsums) cudaFree(c->rowsums);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->copied[i]); cudaEventDestroy(c->consumed[i]); }
@@ -1296,7 +1326,7 @@ int xh_free(int device, void* ptr) {
 }
 int xh_host_alloc(size_t bytes, void** ptr) {
   if (!ptr) return fail(XH_ERR_INVALID, "null");
-  CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+  CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
   return XH_OK;
 }
 int xh_host_free(void* ptr) { CU(cudaFreeHost(ptr)); return XH_OK; }

@@ -268,6 +268,29 @@ __global__ void __launch_bounds__(512) k_peer_allreduce(const __grid_constant__ 
   }
 }
 
+// small results (M * B * 8 bytes up to a few MB): ONE launch, out of place.  G CTAs share a row; every one of them adds up
+// the whole row (the same order in each, so they agree to the bit; the row sits in L2) and scales its own slice into `dst`,
+// which may be pinned host memory — the finished density then lands on the host without a separate copy operation.
+template <bool COUNTS>
+__global__ void __launch_bounds__(1024) k_density_small(const void* src, double* dst, long long B, int G, const __grid_constant__ XhkDensity q) {
+  __shared__ double s_f[32];
+  __shared__ long long s_i[32];
+  const long long r = blockIdx.x / G;
+  const int part = blockIdx.x - static_cast<int>(r) * G;
+  const unsigned char* row = static_cast<const unsigned char*>(src) + static_cast<size_t>(r) * B * 8;
+  double fs = 0.0; long long is = 0;
+  for (long long b = threadIdx.x; b < B; b += blockDim.x) { if (COUNTS) is += reinterpret_cast<const long long*>(row)[b]; else fs += reinterpret_cast<const double*>(row)[b]; }
+  for (int o = 16; o > 0; o >>= 1) { fs += __shfl_xor_sync(0xffffffffu, fs, o); is += __shfl_xor_sync(0xffffffffu, is, o); }
+  if ((threadIdx.x & 31) == 0) { s_f[threadIdx.x >> 5] = fs; s_i[threadIdx.x >> 5] = is; }
+  __syncthreads();
+  fs = 0.0; is = 0;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) { fs += s_f[i]; is += s_i[i]; }
+  const double total = COUNTS ? static_cast<double>(is) : fs;
+  const long long b0 = B * part / G, b1 = B * (part + 1ll) / G;
+  for (long long b = b0 + threadIdx.x; b < b1; b += blockDim.x)
+    dst[r * B + b] = __ddiv_rn(__ddiv_rn(density_load<COUNTS>(row, b), density_area(q, b)), total);
+}
+
 XhkHistKernel pick(int dtype, int w_dtype, int K, int mode) {
   return dtype == 1 ? xhk_pick_hist_f32(w_dtype, K, mode) : dtype == 2 ? xhk_pick_hist_f64(w_dtype, K, mode) : xhk_pick_hist_i64(w_dtype, K, mode);
 }
@@ -399,6 +422,20 @@ cudaError_t xhk_launch_permute(const void* in, void* out, int elem_size, int nd,
   if (blocks > 2147483647ll) return cudaErrorInvalidValue;
   if (elem_size == 4) k_permute_tiled<uint32_t><<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), q);
   else k_permute_tiled<uint64_t><<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const uint64_t*>(in), static_cast<uint64_t*>(out), q);
+  return cudaGetLastError();
+}
+
+cudaError_t xhk_launch_density_small(const void* src, double* dst, long long M, long long B, int counts, const double* widths_dev, const int* nb,
+                                     const int* f32, int K, cudaStream_t s) {
+  XhkDensity q;
+  q.widths = widths_dev; q.K = K;
+  int o = 0;
+  for (int k = 0; k < XHK_MAX_VARS; ++k) { q.off[k] = o; q.nb[k] = k < K ? nb[k] : 1; q.f32[k] = k < K ? f32[k] : 0; if (k < K) o += nb[k]; }
+  if (M <= 0 || B <= 0) return cudaSuccess;
+  const int G = static_cast<int>(std::max<long long>(1, std::min<long long>(std::min<long long>(16, (296 + M - 1) / M), (B + 1023) / 1024)));
+  const int thr = B >= 1024 ? 1024 : static_cast<int>(std::max<long long>(32, (B + 31) / 32 * 32));
+  const unsigned grid = static_cast<unsigned>(M * G);
+  if (counts) k_density_small<true><<<grid, thr, 0, s>>>(src, dst, B, G, q); else k_density_small<false><<<grid, thr, 0, s>>>(src, dst, B, G, q);
   return cudaGetLastError();
 }
 

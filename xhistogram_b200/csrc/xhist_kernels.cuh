@@ -147,6 +147,9 @@ struct XhkPeerArgs {
 cudaError_t xhk_launch_peer_allreduce(const XhkPeerArgs& a, int is_f64, cudaStream_t s);
 // out = C-contiguous transpose(in, perm) of an nd-dimensional array of 4- or 8-byte elements
 cudaError_t xhk_launch_permute(const void* in, void* out, int elem_size, int nd, const long long* shape, const int* perm, cudaStream_t s);
+// the same out of place in one launch, for small results; dst may be pinned host memory (device-mapped)
+cudaError_t xhk_launch_density_small(const void* src, double* dst, long long M, long long B, int counts, const double* widths_dev, const int* nb,
+                                     const int* f32, int K, cudaStream_t s);
 cudaError_t xhk_launch_fill(void* ptr, int dtype, long long n, unsigned long long seed, long long offset, int normal, cudaStream_t s);
 cudaError_t xhk_launch_minmax(const void* data, int dtype, long long n, double* out2_dev, cudaStream_t s);
 cudaError_t xhk_launch_flush(void* buf, size_t bytes, cudaStream_t s);

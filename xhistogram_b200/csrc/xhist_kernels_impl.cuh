@@ -8,6 +8,9 @@
 #ifndef XH_CHEAP_SIDE_W3
 #define XH_CHEAP_SIDE_W3 0
 #endif
+#ifndef XH_DYN_W3
+#define XH_DYN_W3 0      // 1: warps draw their groups from a shared counter in the one-limb weighted fast path (measured: 1.5 % faster at 1.25e8 samples, 2 % slower at 1e9 — more spills; off)
+#endif
 
 namespace {
 
@@ -213,6 +216,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_wlo[XHK_MAX_VARS], s_wlen[XHK_MAX_VARS];
   __shared__ int s_redo;   // fixed point, row owned by this CTA: a weight did not fit -> redo the segment with float64 adds
+  __shared__ unsigned s_next;   // dynamic dealing of the groups of a segment to the warps (see `draw` below)
   __shared__ unsigned s_slow;   // samples of this CTA that left the fast path (window spills, weights outside the fixed-point form)
   // fp32 weights are served by two sibling launches; the probe kernel's verdict (XhkWindow::fx_mode) decides which of
   // them does the work, the other one returns at once (no host round trip between probe and histogram):
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
     }
     s_wlo[tid] = lo; s_wlen[tid] = len;
   }
-  if (tid == 0) { s_redo = 0; s_slow = 0u; }
+  if (tid == 0) { s_redo = 0; s_slow = 0u; s_next = 0u; }
   __syncthreads();
   int wlo[KMAX], wlen[KMAX];
   int wtot = (p.hist_mode == XHK_GLOBAL) ? 0 : 1;
@@ -291,8 +295,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   // an in-range sample that the shared histogram could not take (outside the window, or a weight outside the
   // fixed-point form): global add + one tick of the CTA's slow-path counter.  The host watches the counter to
   // notice a cached probe verdict that no longer fits the data (xhist_api.cu, struct Verdict).
-  unsigned nslow = 0;      // MODE 0 / 2 count in a register, the fused fast paths (rare side loops) in shared memory
-  auto note_slow = [&]() { if constexpr (FAST) atomicAdd(&s_slow, 1u); else ++nslow; };
+  unsigned nslow = 0;      // per thread; summed into s_slow at the end (a shared counter bumped per spill serialises the
+                           // lanes of a warp on one address: data that spills a lot — uniform over the bins — ran 4x slower)
+  auto note_slow = [&]() { ++nslow; };
   auto spill_add = [&](OT* out_row, long long gbin, double wv) { global_add(out_row, gbin, wv); note_slow(); };
   // general path of one sample: exact bins, then shared window / global spill / drop.
   // Returns the window bin when the caller should do the shared add itself, else -1.
@@ -454,6 +459,20 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       int jbias[KMAX];          // fused fast path: window offset of the bin number + RoundSplit::kBias
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) jbias[k] = wlo[k] + RoundSplit<T>::kBias;
+      // How the groups of a segment are dealt to the threads.  Static: thread t takes groups t, t + U * nthr, ... .
+      // Dynamic (one-limb weighted fast path): every warp draws the next 32 * U groups from a shared counter, so the warps
+      // of a CTA reach the end of the segment together instead of up to a few iterations apart (the warps drift: side
+      // loops, bank conflicts) — the CTA waits at the barrier before the flush for its slowest warp.
+      constexpr bool DYN = FAST && W == 3 && (XH_DYN_W3 != 0);
+      const long long ustride = DYN ? 32 : nthr;
+      auto draw = [&]() -> long long {
+        unsigned b = 0;
+        if ((tid & 31) == 0) b = atomicAdd(&s_next, static_cast<unsigned>(U * 32));
+        return static_cast<long long>(__shfl_sync(0xffffffffu, b, 0)) + (tid & 31);
+      };
+      auto first_group = [&]() -> long long { if constexpr (DYN) return draw(); else return tid; };
+      auto next_group = [&](long long g) -> long long { if constexpr (DYN) return draw(); else return g + static_cast<long long>(U) * nthr; };
+      auto group_ok = [&](long long g) -> bool { if constexpr (DYN) return g - (tid & 31) < nvec; else return g < nvec; };   // (warp-uniform when dynamic)
       if constexpr (FAST && W == 0) {
         // ---- counts on the fast path: fused classify + RED, software-pipelined over U register slots of 4 samples
         // per array — a slot is refilled with the group U steps ahead as soon as it has been consumed, so a warp keeps
@@ -583,12 +602,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
           }
         }
       } else
-      for (long long g = tid; g < nvec; g += static_cast<long long>(U) * nthr) {
+      for (long long g = first_group(); group_ok(g); g = next_group(g)) {
         T xv[U][KMAX][4];
         WT wv[U][4];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const long long gu = g + static_cast<long long>(u) * nthr;
+          const long long gu = g + static_cast<long long>(u) * ustride;
           if (gu < nvec) {
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) load4(px[k] + head, gu, xv[u][k]);
@@ -687,12 +706,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
           unsigned worst = 0;
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const bool live = (u == 0) || (g + static_cast<long long>(u) * nthr < nvec);
+            const bool live = g + static_cast<long long>(u) * ustride < nvec;
             unsigned vv[4], old[4];
             bool any_rare = false;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              bool good = live; int wbin = local_row(head + 4 * (g + static_cast<long long>(u) * nthr) + e);
+              bool good = live; int wbin = local_row(head + 4 * (g + static_cast<long long>(u) * ustride) + e);
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) {
                 const T r = fma_t(xv[u][k][e] - Consts<T>::get(p, k, XHK_C_E0), Consts<T>::get(p, k, XHK_C_INV), T(-0.5));
@@ -751,7 +770,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             for (int u = 0; u < U; ++u)
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                side |= (static_cast<int>(idx[u][e]) < 0 && g + static_cast<long long>(u) * nthr < nvec) ? (1u << (4 * u + e)) : 0u;
+                side |= (static_cast<int>(idx[u][e]) < 0 && g + static_cast<long long>(u) * ustride < nvec) ? (1u << (4 * u + e)) : 0u;
             while (side) {
               const int sidx = __ffs(side) - 1;
               side &= side - 1;
@@ -768,7 +787,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 #if XH_CHEAP_SIDE_W3
               // experiment switch (make EXTRA=-DXH_CHEAP_SIDE_W3=1, tools/erratic_probe.sh): fast at best (2.10 ms, 0.87 of
               // the HBM peak on config 3) but erratic, identical launches take 2.1 to 4.3 ms; see DESIGN.md section 8
-              side_uniform(x, wsel, local_row(head + 4 * (g + static_cast<long long>(sidx >> 2) * nthr) + (sidx & 3)), out_row);
+              side_uniform(x, wsel, local_row(head + 4 * (g + static_cast<long long>(sidx >> 2) * ustride) + (sidx & 3)), out_row);
 #else
               // (the straight-line side_uniform() of the count path measured UNSTABLE here: identical launches took
               //  2.1 to 4.0 ms; with this call-based exact path they take 2.21 ms every time)
@@ -782,7 +801,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
               if (sure && !tiled && p.hist_mode != XHK_FULL) spill_add(out_row, gbin, static_cast<double>(wsel));
               else {
                 const int wbin = general_sample(x, static_cast<double>(wsel), out_row,
-                                                local_row(head + 4 * (g + static_cast<long long>(sidx >> 2) * nthr) + (sidx & 3)));
+                                                local_row(head + 4 * (g + static_cast<long long>(sidx >> 2) * ustride) + (sidx & 3)));
                 if (wbin >= 0) shared_add1(wbin, wsel, out_row);
               }
 #endif
@@ -939,8 +958,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       const bool full = p.hist_mode == XHK_FULL;
       unsigned int* lo32 = reinterpret_cast<unsigned int*>(shist);
       unsigned int* hi32 = lo32 + wcap;
-      for (int b = tid; b < wtot; b += nthr) {
-        OT v; bool nz;
+      // value of shared bin b (cleared on the way out)
+      auto take = [&](int b, bool& nz) -> OT {
+        OT v;
         if constexpr (W == 0) { v = static_cast<OT>(shist[b]); nz = v != 0; shist[b] = 0u; }
         else if constexpr (W == 3) { const unsigned q = lo32[b]; nz = q != 0u; v = static_cast<double>(q) * fx_unmul; lo32[b] = 0u; }
         else if (fx) {
@@ -948,14 +968,39 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
           nz = iv != 0; v = static_cast<double>(iv) * fx_unmul;
           lo32[b] = 0u; hi32[b] = 0u;
         } else { v = shist[b]; nz = v != 0.0; shist[b] = 0.0; }
-        if (owned) out_row[b] = v;
-        else if (nz) atomicAdd(out_row + (full ? static_cast<long long>(b) : window_to_global(b)), v);
+        return v;
+      };
+      const int L = (K > 0) ? wlen[K - 1] : 1;          // bins of the last variable inside the window: contiguous in `out`
+      if (owned) {
+        for (int b = tid; b < wtot; b += nthr) { bool nz; const OT v = take(b, nz); out_row[b] = v; }
+      } else if (!full && L >= 32) {
+        // windowed flush, one window row (L contiguous output bins) per warp trip: the window -> global index needs its
+        // divisions once per row instead of once per bin, and every CTA starts at a different row so that the CTAs
+        // of a launch (which all flush at about the same time) do not walk the same output addresses in step
+        const int rows = wtot / L, lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+        const int start = static_cast<int>((static_cast<long long>(blockIdx.x) * rows) / gridDim.x);
+        for (int i = wid; i < rows; i += nw) {
+          int row = i + start; if (row >= rows) row -= rows;
+          const long long gbase = window_to_global(row * L);
+          for (int c = lane; c < L; c += 32) {
+            bool nz; const OT v = take(row * L + c, nz);
+            if (nz) atomicAdd(out_row + gbase + c, v);
+          }
+        }
+      } else {
+        const int start = static_cast<int>((static_cast<long long>(blockIdx.x) * wtot) / gridDim.x) & ~31;
+        for (int i = tid; i < wtot; i += nthr) {
+          int b = i + start; if (b >= wtot) b -= wtot;
+          bool nz; const OT v = take(b, nz);
+          if (nz) atomicAdd(out_row + (full ? static_cast<long long>(b) : window_to_global(b)), v);
+        }
       }
     }
     fx = fx_launch;     // (a redone segment ran with float64 adds)
+    if (tid == 0) s_next = 0u;
     __syncthreads();
   }
-  if constexpr (!FAST) { if (nslow) atomicAdd(&s_slow, nslow); }
+  if (nslow) atomicAdd(&s_slow, nslow);
   __syncthreads();
   if (tid == 0 && s_slow) atomicAdd(p.stats, static_cast<unsigned long long>(s_slow));
 }

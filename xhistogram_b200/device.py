@@ -7,6 +7,7 @@ front-end accepts any object that exposes that interface (C-contiguous fp32/fp64
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import numpy as np
 
@@ -135,6 +136,60 @@ class PinnedArray:
             self.free()
         except Exception:
             pass
+
+
+class _ResultBlock:
+    """One pinned, device-mapped host block lent to a result array: numpy keeps this object as the array's base, and when
+    the array (and every view of it) is gone the block goes back to the pool."""
+
+    __slots__ = ("ptr", "cap", "__array_interface__", "_pool", "__weakref__")
+
+    def __init__(self, pool, ptr, cap, shape, typestr):
+        self._pool, self.ptr, self.cap = pool, ptr, cap
+        self.__array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            self._pool._give(self.ptr, self.cap)
+        except Exception:
+            pass
+
+
+class ResultPool:
+    """Small results (a 256 x 256 float64 histogram is 512 KB) are returned in page-locked host memory that the GPU writes
+    directly (the density kernel stores into it; plain histograms are DMA-ed into it): no staging copy on the host.
+    Blocks are recycled by size class; at most ``limit`` bytes are lent out or cached — beyond that, and for larger
+    results, ordinary pageable arrays are used."""
+
+    def __init__(self, limit=256 << 20, largest=8 << 20):
+        self.limit, self.largest = limit, largest
+        self.free = {}
+        self.total = 0
+
+    def array(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = math.prod(shape) * dtype.itemsize
+        if nbytes == 0 or nbytes > self.largest:
+            return None
+        cap = max(1 << 16, 1 << (nbytes - 1).bit_length())
+        lst = self.free.get(cap)
+        if lst:
+            ptr = lst.pop()
+        else:
+            if self.total + cap > self.limit:
+                return None
+            p = C.c_void_p()
+            if _cabi.lib().xh_host_alloc(cap, C.byref(p)) != 0:
+                return None
+            ptr = p.value
+            self.total += cap
+        return np.asarray(_ResultBlock(self, ptr, cap, tuple(shape), dtype.str))
+
+    def _give(self, ptr, cap):
+        self.free.setdefault(cap, []).append(ptr)
+
+
+result_pool = ResultPool()
 
 
 def is_device_array(a) -> bool:

@@ -31,6 +31,7 @@ extern "C" {
 #define XH_VERSION_MAJOR 0
 #define XH_VERSION_MINOR 1
 #define XH_MAX_VARS 8
+#define XH_MAX_WEIGHTS 4
 
 typedef enum xh_status {
   XH_OK = 0,
@@ -111,6 +112,12 @@ typedef struct xh_desc {
   const double* widths[XH_MAX_VARS];  /* XH_FLAG_DENSITY: HOST np.diff(edges_k) as float64, n_edges[k]-1 values  */
   int32_t widths_f32[XH_MAX_VARS];    /* 1: numpy holds these widths as float32 (a product of two such is
                                          rounded to float32, as np.multiply.outer does in core.py:447-454)      */
+  int32_t n_weights;                  /* 0 / 1: `weights` alone.  2..XH_MAX_WEIGHTS: several weight arrays over the same samples
+                                         in ONE pass (the reference needs one call per weight array: tutorial.ipynb:298-360,
+                                         "TODO: allow list of weights" xarray.py:106): weights, weights_more[0..n_weights-2], all
+                                         of w_dtype and addressed with w_row_stride; out is (n_weights, n_rows, bins) float64   */
+  int32_t reserved2;
+  const void* weights_more[XH_MAX_WEIGHTS - 1];
 } xh_desc;
 
 /* library / device lifecycle --------------------------------------------------------- */

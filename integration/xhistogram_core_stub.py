@@ -25,7 +25,9 @@ class _XhDesc(C.Structure):                       # struct xh_desc, include/xhis
                 ("iedges", C.c_void_p * _XH_MAX_VARS),                # int64 edges for dtype XH_I64 (datetime64, integers)
                 ("n_inner", C.c_int64),                               # > 1: column layout (leading axes reduced)
                 ("widths", C.c_void_p * _XH_MAX_VARS),                # XH_FLAG_DENSITY: np.diff(edges_k) as float64
-                ("widths_f32", C.c_int32 * _XH_MAX_VARS)]             # 1: numpy holds those widths as float32
+                ("widths_f32", C.c_int32 * _XH_MAX_VARS),             # 1: numpy holds those widths as float32
+                ("n_weights", C.c_int32), ("reserved2", C.c_int32),   # > 1: several weight arrays in one pass
+                ("weights_more", C.c_void_p * 3)]
 
 
 def _load(path=None):

@@ -30,7 +30,8 @@ def test_header_symbols_are_exported_and_bound():
 def test_version_and_desc_layout():
     assert _cabi.lib().xh_version() == 1
     # struct xh_desc: 8 int32 + 2 int64 + 8 ptr + 8 int64 + ptr + int64 + 8 ptr + 8 int32 + 3 ptr + 8 ptr + int64 + 8 ptr + 8 int32
-    assert C.sizeof(_cabi.XhDesc) == 32 + 16 + 64 + 64 + 8 + 8 + 64 + 32 + 24 + 64 + 8 + 64 + 32
+    #                 + 2 int32 + 3 ptr (n_weights, reserved2, weights_more)
+    assert C.sizeof(_cabi.XhDesc) == 32 + 16 + 64 + 64 + 8 + 8 + 64 + 32 + 24 + 64 + 8 + 64 + 32 + 8 + 24
     assert _cabi.lib().xh_desc_size() == C.sizeof(_cabi.XhDesc)      # the C compiler agrees with the ctypes mirror
 
 

@@ -178,3 +178,23 @@ def test_dask_inputs_need_explicit_edges(backend):                              
     h, _ = core.histogram(a, bins=np.linspace(-4, 4, 9), density=True)
     want = np.histogram(np.asarray(a), bins=np.linspace(-4, 4, 9), density=True)[0]
     np.testing.assert_allclose(np.asarray(h), want)
+
+
+def test_dask_chunks_are_dealt_to_devices_in_turn(monkeypatch):                      # chunk -> device round-robin
+    import dask.array as dsa
+    seen = []
+
+    def recording_desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, *rest, **kw):
+        seen.append(device)
+        return _oracle_desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, *rest, **kw)
+
+    monkeypatch.setattr(core, "_desc_call", recording_desc_call)
+    a = dsa.from_array(np.random.RandomState(6).randn(12, 10), chunks=(3, 5))            # 4 x 2 = 8 chunks
+    bins = np.linspace(-4, 4, 9)
+    core.set_chunk_devices([0, 1, 2, 3])
+    try:
+        h, _ = core.histogram(a, bins=bins)
+    finally:
+        core.set_chunk_devices(None)
+    np.testing.assert_array_equal(np.asarray(h), np.histogram(np.asarray(a), bins=bins)[0])
+    assert len(seen) == 8 and sorted(set(seen)) == [0, 1, 2, 3] and all(seen.count(d) == 2 for d in range(4))

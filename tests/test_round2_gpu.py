@@ -213,3 +213,84 @@ def test_host_pipeline_reprobes_for_nonstationary_data():
     assert_hist_equal(got, want, rtol=1e-6)
     wc, _ = O.histogram(x, y, bins=[e, e], threads=8)
     assert np.array_equal(core.histogram(x, y, bins=[e, e])[0], wc)
+
+
+def test_int_bins_on_host_arrays_cross_pcie_once():
+    """bins=<int> without a range: the host arrays are uploaded once and both passes (min/max, histogram) read the device copy."""
+    r = np.random.default_rng(41)
+    x = r.standard_normal(2_000_003).astype(np.float32)
+    y = (r.standard_normal(2_000_003) * 3).astype(np.float32)
+    w = r.random(2_000_003).astype(np.float32)
+    h, e = core.histogram(x, bins=50)
+    hw, ew = np.histogram(x, bins=50)
+    assert e[0].dtype == ew.dtype and np.array_equal(e[0], ew) and np.array_equal(h, hw)
+    edges_y = np.linspace(-9, 9, 31)
+    h2, e2 = core.histogram(x, y, bins=[40, edges_y], weights=w, density=True)
+    want, ex, ey = np.histogram2d(x, y, bins=[np.histogram_bin_edges(x, 40), edges_y], weights=w, density=True)
+    assert np.array_equal(e2[0], ex)
+    assert_hist_equal(h2, want, rtol=1e-6)
+    xr_ = x.reshape(-1, 1)[:2_000_000].reshape(1000, 2000)
+    h3, e3 = core.histogram(xr_, bins=25, axis=1)
+    want3 = np.stack([np.histogram(row, bins=np.histogram_bin_edges(xr_, 25))[0] for row in xr_])
+    assert np.array_equal(h3, want3)
+
+
+def test_nccl_minmax_and_file_bootstrap_single_rank(tmp_path, monkeypatch):
+    from xhistogram_b200 import distributed as D
+    monkeypatch.setenv("RANK", "0"); monkeypatch.setenv("WORLD_SIZE", "1"); monkeypatch.setenv("LOCAL_RANK", "0")
+    comm = D.NcclCommunicator.from_env()
+    try:
+        assert comm.allreduce_minmax(-1.5, 2.5) == (-1.5, 2.5)
+        x = np.random.default_rng(3).standard_normal(100_000).astype(np.float32)
+        h, e = D.histogram(x, bins=20, comm=comm)
+        hw, ew = np.histogram(x, bins=20)
+        assert np.array_equal(e[0], ew) and np.array_equal(h, hw)
+    finally:
+        comm.close()
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+@pytest.mark.parametrize("case", ["flat_2d_fits", "rows", "flat_big_bins", "f64_three_weights"])
+def test_list_of_weights_one_pass(where, case):
+    """weights=[w1, w2, ...]: one pass, one histogram per weight array; equals separate oracle calls."""
+    r = np.random.default_rng(50)
+    if case == "flat_2d_fits":
+        shape, edges, wdt, nw, axis = (1_000_003,), [np.linspace(-3, 3, 101), np.linspace(-3, 3, 81)], np.float32, 2, None
+    elif case == "rows":
+        shape, edges, wdt, nw, axis = (37, 20_001), [np.linspace(-3, 3, 41)], np.float32, 3, 1
+    elif case == "flat_big_bins":          # 2 x 256 x 256 float64 planes do not fit shared memory: global adds
+        shape, edges, wdt, nw, axis = (400_000,), [np.linspace(-3, 3, 257), np.linspace(-3, 3, 257)], np.float32, 2, None
+    else:
+        shape, edges, wdt, nw, axis = (300_001,), [np.sort(r.uniform(-3, 3, 30))], np.float64, 3, None
+    ddt = np.float64 if case == "f64_three_weights" else np.float32
+    args = [r.standard_normal(shape).astype(ddt) for _ in edges]
+    ws = [r.standard_normal(shape).astype(wdt) for _ in range(nw)]
+    ws[0][...] = 1.0                                             # plane 0 = the counts, as floats
+    if where == "device":
+        a_in, w_in = [DeviceArray.from_numpy(a) for a in args], [DeviceArray.from_numpy(w) for w in ws]
+    else:
+        a_in, w_in = args, ws
+    h, _ = core.histogram(*a_in, bins=edges, axis=axis, weights=w_in)
+    assert h.shape[0] == nw
+    for q in range(nw):
+        want, _ = O.histogram(*args, bins=edges, axis=axis, weights=ws[q])
+        assert_hist_equal(h[q], want, rtol=1e-6)
+    counts, _ = O.histogram(*args, bins=edges, axis=axis)
+    assert np.array_equal(h[0], counts.astype(np.float64))
+    hd, _ = core.histogram(*a_in, bins=edges, axis=axis, weights=w_in[:2], density=True)
+    for q in range(2):
+        want, _ = O.histogram(*args, bins=edges, axis=axis, weights=ws[q], density=True)
+        assert_hist_equal(hd[q], want, rtol=1e-6)
+
+
+def test_list_of_weights_weighted_mean_of_the_tutorial():
+    """hist(w * a) / hist(w) in one pass (reference tutorial.ipynb:298-360 does two passes over the same samples)."""
+    r = np.random.default_rng(51)
+    a = r.standard_normal(500_000).astype(np.float32)
+    t = (20 + 5 * r.standard_normal(500_000)).astype(np.float32)
+    vol = r.random(500_000).astype(np.float32)
+    e = np.linspace(-3, 3, 61)
+    h, _ = core.histogram(a, bins=e, weights=[vol * t, vol])
+    num, _ = O.histogram(a, bins=e, weights=vol * t)
+    den, _ = O.histogram(a, bins=e, weights=vol)
+    np.testing.assert_allclose(h[0] / h[1], num / den, rtol=1e-9)

@@ -12,6 +12,7 @@ import os
 import threading
 
 XH_MAX_VARS = 8
+XH_MAX_WEIGHTS = 4
 XH_NONE, XH_F32, XH_F64, XH_I64 = 0, 1, 2, 3
 XH_HOST, XH_DEVICE = 0, 1
 XH_FLAG_NO_ZERO = 1
@@ -62,6 +63,9 @@ class XhDesc(C.Structure):
         ("n_inner", C.c_int64),
         ("widths", C.c_void_p * XH_MAX_VARS),         # const double* [XH_MAX_VARS]
         ("widths_f32", C.c_int32 * XH_MAX_VARS),
+        ("n_weights", C.c_int32),
+        ("reserved2", C.c_int32),
+        ("weights_more", C.c_void_p * (XH_MAX_WEIGHTS - 1)),
     ]
 
 

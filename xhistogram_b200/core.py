@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
+import itertools
 import math
 from collections.abc import Iterable
 
@@ -231,6 +232,26 @@ def set_default_device(device: int):
     _default_dev = int(device)
 
 
+_chunk_devices = None
+_chunk_counter = itertools.count()
+
+
+def set_chunk_devices(devices):
+    """Spread independent host-resident blocks over several GPUs: every ``_bincount`` call that is not told where to run
+    (dask's ``blockwise`` maps it over chunks from its worker threads, core.py:429-437) takes the next device of
+    ``devices`` in turn.  The native library keeps one context (stream, staging buffers, lock) per device, so chunks
+    assigned to different GPUs run concurrently; their partial histograms (a few KB to MB) come back to the host, where
+    dask's ``.sum`` over the chunk axes adds them (core.py:439).  ``None`` restores the single default device."""
+    global _chunk_devices
+    _chunk_devices = None if devices is None else [int(d) for d in devices]
+
+
+def _next_chunk_device():
+    if not _chunk_devices:
+        return None
+    return _chunk_devices[next(_chunk_counter) % len(_chunk_devices)]
+
+
 _MIN_INNER_COLUMNS = 32
 
 
@@ -295,6 +316,10 @@ def _bincount(*all_arrays, weights=False, axis=None, bins=None, density=None, bl
         return _bincount_device(all_arrays, w, shape, nd, full, axis, bins, kept_axes_shape, nbins,
                                 _flags, _timing, _out_device, _density_widths)
 
+    if _devices is None:
+        d = _next_chunk_device()
+        if d is not None:
+            _devices = [d]
     raw = [np.asarray(a) for a in all_arrays]
     iplan = _int64_plan(raw, bins)
     if iplan is not None:
@@ -474,7 +499,7 @@ def _edge_info(b):
 
 
 def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing, out_device=None,
-               n_inner=0, density_widths=None, infos=None):
+               n_inner=0, density_widths=None, infos=None, w_more=None):
     K = len(arrs)
     if K > _cabi.XH_MAX_VARS:
         raise NotImplementedError(f"at most {_cabi.XH_MAX_VARS} variables are supported")
@@ -503,6 +528,12 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
         d.w_row_stride = wstride
         if mem == _cabi.XH_HOST and not w.size:
             d.w_dtype = _cabi.XH_NONE
+    nw = 1
+    if w_more:                                            # several weight arrays over the same samples, one pass
+        nw = 1 + len(w_more)
+        d.n_weights = nw
+        for q, wq in enumerate(w_more):
+            d.weights_more[q] = wq.ctypes.data if mem == _cabi.XH_HOST else wq
     if density_widths is not None:
         # density on the device: widths as float64 values plus how numpy holds them (float32 products round to float32)
         d.flags |= _cabi.XH_FLAG_DENSITY
@@ -525,12 +556,12 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
             out = np.empty((M, B), dtype=odt)
             out[...] = np.nan if (density_widths is not None and B) else 0      # 0 / area / 0, as numpy computes it
             return out
-        out = result_pool.array((M, B), odt) if (devices is None or len(devices) <= 1) else None
+        out = result_pool.array((nw * M, B), odt) if (devices is None or len(devices) <= 1) else None
         if out is not None:
             d.flags |= _cabi.XH_FLAG_OUT_PINNED            # page-locked, device-mapped: the GPU writes the result in place
             d.out = out.__array_interface__["data"][0]
         else:
-            out = np.empty((M, B), dtype=odt)
+            out = np.empty((nw * M, B), dtype=odt)
             d.out = out.ctypes.data
     ms = None
     if timing is None and _timing_sink is not None and not (d.flags & _cabi.XH_FLAG_ASYNC):
@@ -555,6 +586,72 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
 # --------------------------------------------------------------------------------------------
 # public entry point (reference: core.py:250-466)
 # --------------------------------------------------------------------------------------------
+def _histogram_weight_list(args, bins, range, axis, weights, density):
+    """``weights=[w1, w2, ...]``: histograms of the SAME samples under several weight arrays in one pass over the data
+    (the reference needs one call per weight array — e.g. the weighted mean of its tutorial, histogram(weights=w*a) /
+    histogram(weights=w), tutorial.ipynb:298-360; "TODO: allow list of weights", xarray.py:106).  The samples are read
+    and classified once; ``hist`` gains a leading axis of length ``len(weights)``.  Host or device-resident inputs;
+    device-resident inputs must reduce all or the trailing axes."""
+    nw = len(weights)
+    if not 2 <= nw <= _cabi.XH_MAX_WEIGHTS:
+        raise ValueError(f"a list of weights takes 2 to {_cabi.XH_MAX_WEIGHTS} arrays")
+    n_inputs = len(args)
+    device = is_device_array(args[0])
+    if device:
+        everything = list(args) + list(weights)
+        if not all(is_device_array(a) for a in everything):
+            raise TypeError("cannot mix device-resident and host arrays in one call")
+        views = [as_device_view(a) for a in everything]
+        shape = views[0][1]
+        if any(v[1] != shape for v in views):
+            raise ValueError("device inputs must all have the same shape")
+        if len({v[2] for v in views[:n_inputs]}) != 1 or len({v[2] for v in views[n_inputs:]}) != 1:
+            raise TypeError("the data arrays must share one dtype, and so must the weight arrays")
+        xdt, wdt = _xh_dtype(views[0][2]), _xh_dtype(views[n_inputs][2])
+        _wait_for_producers(everything, views[0][3])
+    else:
+        everything = list(np.broadcast_arrays(*[np.asarray(a) for a in list(args) + list(weights)]))
+        shape = everything[0].shape
+    ndim = len(shape)
+    axis = _normalise_axis(axis, ndim)
+    bins = _ensure_correctly_formatted_bins(bins, n_inputs)
+    range = _ensure_correctly_formatted_range(range, n_inputs)
+    if any(isinstance(b, str) for b in bins):
+        raise TypeError("string bin estimators are not available with a list of weights")
+    bins = [_resolve_edges(a, b, r, None) for a, b, r in zip(everything[:n_inputs], bins, range)]
+    nbins = tuple(len(b) - 1 for b in bins)
+    full = axis is None or set(axis) == set(_range(ndim))
+    kept_shape = () if full else tuple(shape[i] for i in _range(ndim) if i not in axis)
+    if device:
+        if not full and sorted(axis) != list(_range(ndim - len(axis), ndim)):
+            raise NotImplementedError("a list of weights on device-resident inputs reduces all axes or the trailing axes")
+        N = int(math.prod(shape)) if full else int(math.prod(shape[ndim - len(axis):]))
+        M = int(math.prod(shape)) // N if N else int(math.prod(kept_shape))
+        ptrs = [v[0] for v in views]
+        out = _desc_call(ptrs[:n_inputs], [N] * n_inputs, ptrs[n_inputs], N, bins, M, N, xdt, wdt, _cabi.XH_DEVICE, views[0][3],
+                         None, 0, None, w_more=ptrs[n_inputs + 1:])
+    else:
+        data = [_as_float_data(a) for a in everything[:n_inputs]]
+        if len({a.dtype for a in data}) > 1:
+            data = [a.astype(np.float64) for a in data]
+        ws = [_as_float_weights(w) for w in everything[n_inputs:]]
+        if len({w.dtype for w in ws}) > 1:
+            ws = [w.astype(np.float64) for w in ws]
+        ax = None if full else list(axis)
+        rows = [_rows_view(a, ax, full) for a in data]
+        M, N = rows[0][2], rows[0][3]
+        wrows = [_rows_view(w, ax, full) for w in ws]
+        if len({r[1] for r in wrows}) != 1:                      # one addressing for all weight arrays: materialise broadcast rows
+            wrows = [(np.ascontiguousarray(np.broadcast_to(r[0], (M, N))), N, M, N) for r in wrows]
+        out = _desc_call([r[0] for r in rows], [r[1] for r in rows], wrows[0][0], wrows[0][1], bins, M, N, _xh_dtype(data[0].dtype),
+                         _xh_dtype(wrows[0][0].dtype), _cabi.XH_HOST, _default_device(), None, 0, None, w_more=[r[0] for r in wrows[1:]])
+    h = out.reshape((nw,) + kept_shape + nbins)
+    if density:
+        areas = functools.reduce(np.multiply.outer, [np.diff(b) for b in bins])
+        h = h / areas / h.sum(axis=tuple(_range(-n_inputs, 0)), keepdims=True)
+    return h, bins
+
+
 def _normalise_axis(axis, ndim):
     if axis is None:                                                 # core.py:341-352
         return None
@@ -566,6 +663,30 @@ def _normalise_axis(axis, ndim):
         assert ax_positive < ndim, "axis must be less than ndim"
         axis_normed.append(int(ax_positive))
     return axis_normed
+
+
+_UPLOAD_LIMIT_BYTES = 32 << 30
+
+
+def _upload_pays(args, weights, bins, range_):
+    """True for host float arrays of one shape and dtype, C-contiguous, when some argument takes bins=<int> from its data range."""
+    if range_ is not None or bins is None:
+        return False
+    blist = bins if isinstance(bins, (list, tuple)) else [bins] * len(args)
+    if len(blist) != len(args) or not any(isinstance(b, (int, np.integer)) and not isinstance(b, bool) for b in blist):
+        return False
+    if any(isinstance(b, str) for b in blist):
+        return False
+    every = list(args) + ([weights] if weights is not None else [])
+    a0 = every[0]
+    if a0.size < (1 << 16) or a0.dtype not in (np.float32, np.float64):
+        return False
+    total = 0
+    for a in every:
+        if a.shape != a0.shape or not a.flags.c_contiguous or a.dtype not in (np.float32, np.float64):
+            return False
+        total += a.nbytes
+    return all(a.dtype == a0.dtype for a in args) and total <= _UPLOAD_LIMIT_BYTES
 
 
 def _histogram_device(args, bins, range, axis, weights, density, out):
@@ -615,7 +736,9 @@ def histogram(*args, bins=None, range=None, axis=None, weights=None, density=Fal
               devices=None, out=None):
     """Histogram applied along specified axis / axes — signature of ``xhistogram.core.histogram``.
 
-    Parameters are those of the reference (see its docstring, core.py:259-333).  Extensions, both optional:
+    Parameters are those of the reference (see its docstring, core.py:259-333).  Extensions, all optional:
+    ``weights`` may be a list of 2-4 arrays: one pass over the samples, ``hist`` gains a leading axis (one histogram per
+    weight array; see ``_histogram_weight_list``);
     ``devices`` — list of CUDA ordinals to shard a host-resident request over (rows are split when enough rows are
     kept, otherwise the reduced axis is split and the partial histograms are summed with NCCL);
     ``out`` — for device-resident inputs, a ``DeviceArray`` of 8-byte items that receives the result: the call
@@ -628,6 +751,10 @@ def histogram(*args, bins=None, range=None, axis=None, weights=None, density=Fal
         raise TypeError("histogram() needs at least one array")
     if block_size is not None and block_size != "auto" and not isinstance(block_size, (int, np.integer)):
         raise TypeError("block_size must be None, an int or 'auto'")
+    if isinstance(weights, (list, tuple)):
+        if out is not None or devices is not None:
+            raise TypeError("a list of weights cannot be combined with out= or devices=")
+        return _histogram_weight_list(args, bins, range, axis, weights, density)
     if is_device_array(args[0]):
         return _histogram_device(args, bins, range, axis, weights, density, out)
     if out is not None:
@@ -639,6 +766,18 @@ def histogram(*args, bins=None, range=None, axis=None, weights=None, density=Fal
     if not is_dask_array:
         args = tuple(np.asarray(a) for a in args)
         weights = None if weights is None else np.asarray(weights)
+
+    if not is_dask_array and devices is None and _upload_pays(args, weights, bins, range):
+        # bins=<int> without a range needs min/max of the data before the histogram: two passes.  Host arrays that fit
+        # comfortably in HBM cross PCIe ONCE — upload, reduce and histogram from the device copy — instead of once per
+        # pass (the reference reads the host array twice as well: np.histogram_bin_edges, then _bincount; core.py:383-388)
+        dev = _default_device()
+        staged = [DeviceArray.from_numpy(a, dev) for a in args] + ([DeviceArray.from_numpy(weights, dev)] if weights is not None else [])
+        try:
+            return _histogram_device(tuple(staged[: len(args)]), bins, range, axis, staged[len(args)] if weights is not None else None, density, None)
+        finally:
+            for t in staged:
+                t.free()
 
     a0 = args[0]
     ndim = len(as_device_view(a0)[1]) if device_inputs else a0.ndim

@@ -693,6 +693,14 @@ int validate(const xh_desc* d) {
     return fail(XH_ERR_INVALID, "XH_FLAG_ASYNC needs device data, a device out and no kernel_ms");
   if (d->n_inner > 1 && (d->n_rows % d->n_inner) != 0) return fail(XH_ERR_INVALID, "column layout: n_rows must be a multiple of n_inner");
   if (d->n_inner < 0) return fail(XH_ERR_INVALID, "negative n_inner");
+  if (d->n_weights < 0 || d->n_weights > XH_MAX_WEIGHTS) return fail(XH_ERR_INVALID, "n_weights must be 0..%d", XH_MAX_WEIGHTS);
+  if (d->n_weights > 1) {
+    if (!d->weights || d->w_dtype == XH_NONE) return fail(XH_ERR_INVALID, "n_weights > 1 needs weights and w_dtype");
+    for (int q = 0; q + 1 < d->n_weights; ++q)
+      if (!d->weights_more[q] || reinterpret_cast<uintptr_t>(d->weights_more[q]) % dsize(d->w_dtype)) return fail(XH_ERR_INVALID, "weights_more[%d] is null or misaligned", q);
+    if (d->flags & (XH_FLAG_DENSITY | XH_FLAG_NO_ZERO)) return fail(XH_ERR_UNSUPPORTED, "several weight arrays: the density is taken per plane on the caller side, and the planes are zero-filled by the library");
+    if (d->n_inner > 1) return fail(XH_ERR_UNSUPPORTED, "several weight arrays are not available in the column layout");
+  }
   if (d->flags & XH_FLAG_DENSITY) {
     if (d->flags & XH_FLAG_NO_ZERO) return fail(XH_ERR_INVALID, "XH_FLAG_DENSITY cannot be combined with XH_FLAG_NO_ZERO");
     for (int k = 0; k < d->n_vars; ++k) if (!d->widths[k]) return fail(XH_ERR_INVALID, "XH_FLAG_DENSITY needs widths[%d]", k);
@@ -729,8 +737,34 @@ int choose_tile_rows(Ctx* c, const Prep& pr, const xh_desc* d) {
   return R >= 2 ? static_cast<int>(R) : 1;
 }
 
-int run_device_block(Ctx* c, const PrepEntry& pe, const xh_desc* d, cudaStream_t stream, bool cache) {
+// several weight arrays in one pass: k_hist_mw; `planes` = elements between two weight planes of the output
+int run_mw_device(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, long long planes, bool zero) {
+  XhkParams p = pr.base;
+  p.M = d->n_rows; p.N = d->n_cols;
+  for (int k = 0; k < d->n_vars; ++k) { p.data[k] = d->data[k]; p.stride[k] = d->row_stride[k]; }
+  p.w = d->weights; p.wstride = d->w_row_stride; p.out = d->out; p.edges = pr.dev_edges; p.w_dtype = d->w_dtype;
+  p.lut = reinterpret_cast<const unsigned short*>(static_cast<const unsigned char*>(pr.dev_edges) + pr.lut_dev_off);
+  p.stats = c->dummy_stats;
+  XhkMultiWeights m = {};
+  m.nw = d->n_weights; m.w[0] = d->weights;
+  for (int q = 1; q < m.nw; ++q) m.w[q] = d->weights_more[q - 1];
+  const size_t hist_bytes = static_cast<size_t>(m.nw) * pr.base.B * 8;
+  const long long budget = static_cast<long long>(c->smem_optin) - 64 - static_cast<long long>(pr.edges_al);
+  m.use_smem = (static_cast<long long>(hist_bytes) <= budget && !(d->flags & XH_FLAG_FORCE_GLOBAL)) ? 1 : 0;
+  m.chunk = 1 << 14;
+  m.plane = planes;          // elements between the planes of the output (a row block of a larger output passes the whole M * B)
+  if (zero) CU(cudaMemsetAsync(d->out, 0, static_cast<size_t>(m.nw) * p.M * p.B * 8, stream));
+  const long long items = p.M * ((p.N + m.chunk - 1) / m.chunk);
+  XhkLaunch l; l.dtype = d->dtype; l.w_dtype = d->w_dtype; l.threads = XHK_THREADS; l.stream = stream;
+  l.smem_bytes = pr.edges_al + (m.use_smem ? hist_bytes : 0) + 16;
+  l.grid = static_cast<int>(std::max<long long>(1, std::min<long long>(items, c->sm_count)));
+  CU(xhk_launch_hist_mw(p, m, l));
+  return XH_OK;
+}
+
+int run_device_block(Ctx* c, const PrepEntry& pe, const xh_desc* d, cudaStream_t stream, bool cache, long long mw_planes = 0) {
   const Prep& pr = pe.pr;
+  if (d->n_weights > 1) return run_mw_device(c, pr, d, stream, mw_planes ? mw_planes : d->n_rows * pr.base.B, !(d->flags & XH_FLAG_NO_ZERO));
   const int R = choose_tile_rows(c, pr, d);
   if (R > 1) {
     const long long M = d->n_rows, N = d->n_cols, tiles = M / R, rem = M % R;
@@ -756,8 +790,12 @@ int run_host_pipeline(Ctx* c, const PrepEntry& pe, const xh_desc* d, void* dev_o
   const int K = d->n_vars;
   const size_t tsz = dsize(d->dtype), wsz = dsize(d->w_dtype);
   const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
-  const int narr = K + (wsz ? 1 : 0);
-  auto arr_ptr = [&](int a) -> const unsigned char* { return static_cast<const unsigned char*>(a < K ? d->data[a] : d->weights); };
+  const int nwt = wsz ? (d->n_weights > 1 ? d->n_weights : 1) : 0;       // weight arrays
+  const bool mw = nwt > 1;
+  const int narr = K + nwt;
+  auto arr_ptr = [&](int a) -> const unsigned char* {
+    return static_cast<const unsigned char*>(a < K ? d->data[a] : a == K ? d->weights : d->weights_more[a - K - 1]);
+  };
   auto arr_stride = [&](int a) -> long long { return a < K ? d->row_stride[a] : d->w_row_stride; };
   auto arr_size = [&](int a) -> size_t { return a < K ? tsz : wsz; };
   const long long chunk = 1ll << 23;  // samples per staged block (32 MiB per fp32 array)
@@ -778,7 +816,7 @@ int run_host_pipeline(Ctx* c, const PrepEntry& pe, const xh_desc* d, void* dev_o
   for (int a = 0; a < narr; ++a) { slot_off[a] = slot_bytes; slot_bytes += (static_cast<size_t>(blk_samples) * arr_size(a) + 255) & ~static_cast<size_t>(255); }
   int rc = ensure_stage(c, slot_bytes);
   if (rc) return rc;
-  if (long_rows) CU(cudaMemsetAsync(dev_out, 0, static_cast<size_t>(M) * B * 8, c->stream));  // column chunks accumulate
+  if (long_rows || mw) CU(cudaMemsetAsync(dev_out, 0, static_cast<size_t>(mw ? nwt : 1) * M * B * 8, c->stream));  // column chunks accumulate
   if (bc_bytes) {
     for (int a = 0; a < narr; ++a)
       if (arr_stride(a) == 0 && M > 1)
@@ -791,7 +829,7 @@ int run_host_pipeline(Ctx* c, const PrepEntry& pe, const xh_desc* d, void* dev_o
     CU(cudaStreamWaitEvent(c->copy_stream, c->consumed[slot], 0));
     xh_desc b = *d;
     b.mem = XH_DEVICE; b.out_mem = XH_DEVICE; b.kernel_ms = nullptr;
-    if (long_rows) b.flags |= XH_FLAG_NO_ZERO;  // whole-row blocks own their slice of out and zero/store it themselves
+    if (long_rows || mw) b.flags |= XH_FLAG_NO_ZERO;  // (otherwise whole-row blocks own their slice of out and zero/store it themselves)
     b.n_rows = nrows; b.n_cols = ncols;
     b.out = static_cast<unsigned char*>(dev_out) + static_cast<size_t>(r0) * B * 8;
     for (int a = 0; a < narr; ++a) {
@@ -808,11 +846,13 @@ int run_host_pipeline(Ctx* c, const PrepEntry& pe, const xh_desc* d, void* dev_o
         else { CU(cudaMemcpy2DAsync(dst, static_cast<size_t>(ncols) * es, src, static_cast<size_t>(st) * es, static_cast<size_t>(ncols) * es, nrows, cudaMemcpyHostToDevice, c->copy_stream)); dev_stride = ncols; }
         dev_ptr = dst;
       }
-      if (a < K) { b.data[a] = dev_ptr; b.row_stride[a] = dev_stride; } else { b.weights = dev_ptr; b.w_row_stride = dev_stride; }
+      if (a < K) { b.data[a] = dev_ptr; b.row_stride[a] = dev_stride; }
+      else if (a == K) { b.weights = dev_ptr; b.w_row_stride = dev_stride; }
+      else { b.weights_more[a - K - 1] = dev_ptr; }        // (all weight arrays share one addressing, so the same dev_stride)
     }
     CU(cudaEventRecord(c->copied[slot], c->copy_stream));
     CU(cudaStreamWaitEvent(c->stream, c->copied[slot], 0));
-    int rc2 = run_device_block(c, pe, &b, c->stream, false);   // new data in the same staging slots: probe every chunk
+    int rc2 = run_device_block(c, pe, &b, c->stream, false, mw ? M * B : 0);   // new data in the same staging slots: probe every chunk
     if (rc2) return rc2;
     CU(cudaEventRecord(c->consumed[slot], c->stream));
     return XH_OK;
@@ -1011,7 +1051,8 @@ int peer_allreduce(Ctx* c, size_t count, bool f64, void* out, cudaStream_t s) {
 int hist_locked(Ctx* c, const xh_desc* d) {
   CU(cudaSetDevice(c->device));
   const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
-  const size_t out_bytes = static_cast<size_t>(M) * B * 8;
+  const int nw = d->n_weights > 1 ? d->n_weights : 1;
+  const size_t out_bytes = static_cast<size_t>(nw) * M * B * 8;
   void* dev_out = d->out;
   if (d->out_mem == XH_HOST && out_bytes) {
     if (out_bytes > c->outbuf_cap) {
@@ -1058,8 +1099,8 @@ int hist_locked(Ctx* c, const xh_desc* d) {
   if (rc == XH_OK && (d->flags & XH_FLAG_ALLREDUCE) && out_bytes) {
     // partial histograms of the ranks -> global histogram on the same stream (no host round trip): one peer-memory
     // kernel for small histograms, ncclAllReduce in place otherwise
-    if (via_peers) rc = peer_allreduce(c, static_cast<size_t>(M * B), d->w_dtype != XH_NONE, final_out, s);
-    else rc = allreduce_in_place(c, dev_out, static_cast<size_t>(M * B), d->w_dtype != XH_NONE, s);
+    if (via_peers) rc = peer_allreduce(c, static_cast<size_t>(nw * M * B), d->w_dtype != XH_NONE, final_out, s);
+    else rc = allreduce_in_place(c, dev_out, static_cast<size_t>(nw * M * B), d->w_dtype != XH_NONE, s);
     dev_out = final_out;
   }
   if (rc == XH_OK && (d->flags & XH_FLAG_DENSITY) && out_bytes) {
@@ -1213,6 +1254,7 @@ int xh_hist_multi(const xh_desc* d, const int32_t* devices, int32_t n_dev) {
   if (n_dev == 1) { xh_desc b = *d; b.device = devices[0]; return xh_hist(&b); }
   if (d->flags & (XH_FLAG_DENSITY | XH_FLAG_ALLREDUCE)) return fail(XH_ERR_UNSUPPORTED, "xh_hist_multi reduces on its own; the density is taken on the caller side");
   if (d->n_inner > 1) return fail(XH_ERR_UNSUPPORTED, "xh_hist_multi does not take the column layout; shard the kept axis on the caller side");
+  if (d->n_weights > 1) return fail(XH_ERR_UNSUPPORTED, "xh_hist_multi does not take several weight arrays");
   const long long M = d->n_rows, N = d->n_cols, B = bins_per_row(d);
   const size_t tsz = dsize(d->dtype), wsz = dsize(d->w_dtype);
   std::vector<Ctx*> ctx(n_dev);

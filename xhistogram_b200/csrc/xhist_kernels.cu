@@ -303,9 +303,14 @@ XhkColsKernel pick_cols(int dtype, int w, int K) {
 
 // Mode 2 (branch-free classification for uniform / bounded-step-table variables) handles records above 16 bytes of
 // data per sample two samples at a time (half groups) to stay inside the 64-register budget; see k_hist.
-int kernel_mode(const XhkParams& p, int dtype) {
+int kernel_mode(const XhkParams& p, int dtype, int w = 0) {
   if (dtype == 3) return 0;
-  if (p.all_uniform) return p.tile_rows > 1 ? 3 : 1;   // row tiling is a compile-time variant of the fast kernel
+  if (p.all_uniform) {
+    if (p.tile_rows > 1) return 3;                       // row tiling is a compile-time variant of the fast kernel
+    // one-limb weights over a short per-CTA range: dynamic dealing of the groups to the warps (see k_hist, MODE 5)
+    if (w == 3 && p.partition == XHK_PART_SAMPLES && p.per_cta <= (5ll << 19)) return 5;
+    return 1;
+  }
   return (p.all_branch_free && p.n_vars <= 4) ? 2 : 0;
 }
 
@@ -317,7 +322,8 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
   for (int dt = 1; dt <= 3; ++dt)
     for (int w = 0; w <= (dt == 3 ? 2 : 3); ++w)
       for (int k = 1; k <= 5; ++k)
-        for (int f = 0; f <= 3; ++f) {
+        for (int f = 0; f <= 5; ++f) {
+          if (f == 4) continue;
           cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick(dt, w, k, f)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
           if (e != cudaSuccess) return e;
         }
@@ -328,6 +334,12 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
         cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_cols(dt, w, k)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
         if (e != cudaSuccess) return e;
       }
+  for (int w = 1; w <= 2; ++w)
+    for (int k = 0; k <= 3; ++k) {
+      const void* fns[3] = {reinterpret_cast<const void*>(xhk_pick_mw_f32(w, k)), reinterpret_cast<const void*>(xhk_pick_mw_f64(w, k)),
+                            reinterpret_cast<const void*>(xhk_pick_mw_i64(w, k))};
+      for (const void* fn : fns) { cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin); if (e != cudaSuccess) return e; }
+    }
   for (int dt = 1; dt <= 3; ++dt)
     for (int k = 0; k <= 4; ++k) {
       cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_window(dt, k)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 192);
@@ -337,8 +349,14 @@ cudaError_t xhk_set_smem_limits(int max_optin) {
 }
 
 cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l) {
-  XhkHistKernel k = pick(l.dtype, l.w_dtype, p.n_vars, kernel_mode(p, l.dtype));
+  XhkHistKernel k = pick(l.dtype, l.w_dtype, p.n_vars, kernel_mode(p, l.dtype, l.w_dtype));
   k<<<l.grid, l.threads, l.smem_bytes, l.stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t xhk_launch_hist_mw(const XhkParams& p, const XhkMultiWeights& m, const XhkLaunch& l) {
+  XhkMwKernel k = l.dtype == 1 ? xhk_pick_mw_f32(l.w_dtype, p.n_vars) : l.dtype == 2 ? xhk_pick_mw_f64(l.w_dtype, p.n_vars) : xhk_pick_mw_i64(l.w_dtype, p.n_vars);
+  k<<<l.grid, l.threads, l.smem_bytes, l.stream>>>(p, m);
   return cudaGetLastError();
 }
 

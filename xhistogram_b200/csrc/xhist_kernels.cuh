@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #define XHK_MAX_VARS 8
+#define XHK_MAX_WEIGHTS 4
 #define XHK_MAX_PEERS 16
 #define XHK_PEER_FLAG_BYTES 4096   // head of every rank's symmetric buffer: one u64 arrival flag per peer
 // threads of a k_hist CTA when one CTA owns an SM (register budget: 65536 / XHK_THREADS per thread)
@@ -112,10 +113,20 @@ struct XhkLaunch {
 typedef void (*XhkHistKernel)(const XhkParams);
 typedef void (*XhkWindowKernel)(const XhkParams, XhkWindow*, int, int, int);
 typedef void (*XhkColsKernel)(const XhkParams, long long, int, int);
+// several weight arrays in one pass (k_hist_mw)
+struct XhkMultiWeights {
+  const void* w[XHK_MAX_WEIGHTS];   // device, addressed like XhkParams::w (row stride XhkParams::wstride)
+  int nw;
+  int use_smem;                     // 1: nw planes of B float64 bins in shared memory; 0: global REDs only
+  long long chunk;                  // samples of the reduced axis per work item (multiple of 4)
+  long long plane;                  // elements between two weight planes of the output
+};
+typedef void (*XhkMwKernel)(const XhkParams, const XhkMultiWeights);
 #define XHK_DECLARE_PICKERS(DT)                                  \
   XhkHistKernel xhk_pick_hist_##DT(int w, int K, int mode);      \
   XhkWindowKernel xhk_pick_window_##DT(int K);                   \
-  XhkColsKernel xhk_pick_cols_##DT(int w, int K);
+  XhkColsKernel xhk_pick_cols_##DT(int w, int K);                \
+  XhkMwKernel xhk_pick_mw_##DT(int w, int K);
 XHK_DECLARE_PICKERS(f32)
 XHK_DECLARE_PICKERS(f64)
 XHK_DECLARE_PICKERS(i64)
@@ -125,6 +136,7 @@ cudaError_t xhk_launch_hist(const XhkParams& p, const XhkLaunch& l);
 // column layout: p.M = n_outer * n_inner logical rows, p.N reduced length, inner = n_inner; tm columns per CTA,
 // nsplit CTAs share the reduced axis of one column tile (nsplit > 1 -> atomic flush into a zeroed out)
 cudaError_t xhk_launch_hist_cols(const XhkParams& p, const XhkLaunch& l, long long inner, int tm, int nsplit, int accumulate);
+cudaError_t xhk_launch_hist_mw(const XhkParams& p, const XhkMultiWeights& m, const XhkLaunch& l);
 cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow* window_dev, int budget_bins, int budget32_bins, int n_probe);
 cudaError_t xhk_launch_zero_shared_rows(const XhkParams& p, const XhkLaunch& l);
 cudaError_t xhk_set_smem_limits(int max_optin);

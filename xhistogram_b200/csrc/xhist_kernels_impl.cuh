@@ -8,9 +8,7 @@
 #ifndef XH_CHEAP_SIDE_W3
 #define XH_CHEAP_SIDE_W3 0
 #endif
-#ifndef XH_DYN_W3
-#define XH_DYN_W3 0      // 1: warps draw their groups from a shared counter in the one-limb weighted fast path (measured: 1.5 % faster at 1.25e8 samples, 2 % slower at 1e9 — more spills; off)
-#endif
+
 
 namespace {
 
@@ -208,7 +206,8 @@ template <> struct WType<2> { using type = double; };
 // ---------------------------------------------------------------------------------------------
 template <typename T, int W, int KT, int MODE>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__ XhkParams p) {
-  constexpr bool FAST = (MODE == 1 || MODE == 3);   // 3: the same with row tiling compiled in (1: compiled out)
+  constexpr bool FAST = (MODE == 1 || MODE == 3 || MODE == 5);   // 3: the same with row tiling compiled in (1: compiled out);
+                                                                  // 5: mode 1 with dynamic dealing of the groups to the warps (W = 3 only)
   using HT = typename std::conditional<W == 0 || W == 3, unsigned int, double>::type;   // shared accumulator
   using OT = typename std::conditional<W == 0, unsigned long long, double>::type;       // global accumulator
   using WT = typename WType<W>::type;
@@ -256,7 +255,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   }
   // row tiling: the shared histogram holds tile_rows rows; a sample's bin is offset by (local row) * (bins per row),
   // obtained for free by seeding the Horner evaluation of the joint bin with the local row
-  const bool tiled = (MODE == 3) || (MODE != 1 && p.tile_rows > 1);
+  const bool tiled = (MODE == 3) || (MODE != 1 && MODE != 5 && p.tile_rows > 1);
   wtot *= p.tile_rows;
   const int hwords = (wtot + 32) * static_cast<int>(sizeof(HT) / 4);               // (+ the trash slots)
   for (int i = tid; i < hwords; i += nthr) hregion[i] = 0u;
@@ -460,10 +459,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) jbias[k] = wlo[k] + RoundSplit<T>::kBias;
       // How the groups of a segment are dealt to the threads.  Static: thread t takes groups t, t + U * nthr, ... .
-      // Dynamic (one-limb weighted fast path): every warp draws the next 32 * U groups from a shared counter, so the warps
-      // of a CTA reach the end of the segment together instead of up to a few iterations apart (the warps drift: side
-      // loops, bank conflicts) — the CTA waits at the barrier before the flush for its slowest warp.
-      constexpr bool DYN = FAST && W == 3 && (XH_DYN_W3 != 0);
+      // Dynamic (MODE 5: one-limb weighted fast path on SHORT per-CTA ranges): every warp draws the next 32 * U groups from
+      // a shared counter, so the warps of a CTA reach the end of the segment together instead of a few iterations apart
+      // (the warps drift: side loops, bank conflicts) and the CTA does not wait at the barrier before the flush for its
+      // slowest warp.  Measured on config 3: 6 % of the kernel at 1.25e8 samples (a 1/8 shard), but the extra live state
+      // costs spills — 2 % slower at 1e9 — so the host picks it only for short ranges (kernel_mode()).
+      constexpr bool DYN = (MODE == 5) && W == 3;
       const long long ustride = DYN ? 32 : nthr;
       auto draw = [&]() -> long long {
         unsigned b = 0;
@@ -1284,6 +1285,114 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist_cols(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// several weight arrays over the SAME samples in one pass (the reference's tutorial computes a weighted mean
+// as histogram(weights=w*a) / histogram(weights=w), two passes over identical samples, and lists "allow list of weights"
+// as a TODO, xarray.py:106).  The samples are read and classified once; every weight array has its own plane of float64
+// bins — [nw][B] in shared memory when that fits (red.shared.add.f64), else straight global REDs.  Work items are
+// (row, chunk of the reduced axis); a CTA walks a contiguous run of items and flushes its planes whenever the row changes.
+// out: [nw][M][B] float64, zero-filled by the host.
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename WT, int KT>
+__global__ void __launch_bounds__(kMaxThreads, 1) k_hist_mw(const __grid_constant__ XhkParams p, const __grid_constant__ XhkMultiWeights m) {
+  constexpr int KMAX = KT ? KT : XHK_MAX_VARS;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int K = KT ? KT : p.n_vars, tid = threadIdx.x, nthr = blockDim.x;
+  T* sedges = reinterpret_cast<T*>(smem);
+  const size_t edges_al = (static_cast<size_t>(p.n_edges_total) * sizeof(T) + 15) & ~static_cast<size_t>(15);
+  unsigned short* slut = reinterpret_cast<unsigned short*>(smem + edges_al);
+  double* hist = reinterpret_cast<double*>(smem + edges_al + ((static_cast<size_t>(p.n_lut_total) * 2 + 15) & ~static_cast<size_t>(15)));
+  for (int i = tid; i < p.n_edges_total; i += nthr) sedges[i] = static_cast<const T*>(p.edges)[i];
+  for (int i = tid; i < p.n_lut_total; i += nthr) slut[i] = p.lut[i];
+  const int B = static_cast<int>(p.B), nw = m.nw;
+  const int hbins = m.use_smem ? nw * B : 0;
+  for (int i = tid; i < hbins; i += nthr) hist[i] = 0.0;
+  __syncthreads();
+  const unsigned sh = static_cast<unsigned>(__cvta_generic_to_shared(hist));
+  double* const out = static_cast<double*>(p.out);
+  const long long plane = m.plane;
+  const long long items_per_row = (p.N + m.chunk - 1) / m.chunk, items = p.M * items_per_row;
+  const long long i0 = items * blockIdx.x / gridDim.x, i1 = items * (blockIdx.x + 1ll) / gridDim.x;
+  long long cur_row = -1;
+  auto flush = [&](long long r) {
+    __syncthreads();
+    for (int i = tid; i < hbins; i += nthr) {
+      const double v = hist[i];
+      if (v != 0.0) { const int q = i / B; atomicAdd(out + q * plane + r * p.B + (i - q * B), v); hist[i] = 0.0; }   // (NaN != 0: flushed)
+    }
+    __syncthreads();
+  };
+  auto one = [&](const T (&x)[KMAX], const WT (&w)[XHK_MAX_WEIGHTS], long long r) {
+    int bin = 0; bool ok = true;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        const int j = exact_bin_inline<T>(p, k, sedges, slut, x[k]);
+        ok = ok && j >= 0;
+        bin = bin * p.nb[k] + j;
+      }
+    }
+    if (!ok) return;
+    if (m.use_smem) { for (int q = 0; q < nw; ++q) reds_add_f64(sh + 8u * static_cast<unsigned>(q * B + bin), static_cast<double>(w[q])); }
+    else { for (int q = 0; q < nw; ++q) atomicAdd(out + q * plane + r * p.B + bin, static_cast<double>(w[q])); }
+  };
+  for (long long it = i0; it < i1; ++it) {
+    const long long r = it / items_per_row, c0 = (it - r * items_per_row) * m.chunk;
+    const long long c1 = c0 + m.chunk < p.N ? c0 + m.chunk : p.N;
+    if (r != cur_row) { if (cur_row >= 0 && hbins) flush(cur_row); cur_row = r; }
+    const T* px[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) px[k] = (k < K) ? static_cast<const T*>(p.data[k]) + r * p.stride[k] : nullptr;
+    const WT* pw[XHK_MAX_WEIGHTS];
+#pragma unroll
+    for (int q = 0; q < XHK_MAX_WEIGHTS; ++q) pw[q] = (q < nw) ? static_cast<const WT*>(m.w[q]) + r * p.wstride : nullptr;
+    bool vec = (KT != 0) && ((c0 & 3) == 0);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) if (k < K) vec = vec && ((reinterpret_cast<uintptr_t>(px[k] + c0) & 15) == 0);
+    for (int q = 0; q < nw; ++q) vec = vec && ((reinterpret_cast<uintptr_t>(pw[q] + c0) & 15) == 0);
+    long long c = c0;
+    if (vec) {
+      const long long nv = (c1 - c0) >> 2;
+      for (long long g = tid; g < nv; g += nthr) {
+        T xv[KMAX][4]; WT wv[XHK_MAX_WEIGHTS][4];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) if (k < K) load4(px[k] + c0, g, xv[k]);
+#pragma unroll
+        for (int q = 0; q < XHK_MAX_WEIGHTS; ++q) if (q < nw) load4(pw[q] + c0, g, wv[q]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          T x[KMAX]; WT w[XHK_MAX_WEIGHTS];
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) x[k] = (k < K) ? xv[k][e] : T(0);
+#pragma unroll
+          for (int q = 0; q < XHK_MAX_WEIGHTS; ++q) w[q] = (q < nw) ? wv[q][e] : WT(0);
+          one(x, w, r);
+        }
+      }
+      c = c0 + (nv << 2);
+    }
+    for (long long i = c + tid; i < c1; i += nthr) {
+      T x[KMAX]; WT w[XHK_MAX_WEIGHTS];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) x[k] = (k < K) ? px[k][i] : T(0);
+#pragma unroll
+      for (int q = 0; q < XHK_MAX_WEIGHTS; ++q) w[q] = (q < nw) ? pw[q][i] : WT(0);
+      one(x, w, r);
+    }
+  }
+  if (cur_row >= 0 && hbins) flush(cur_row);
+}
+
+template <typename T, typename WT>
+XhkMwKernel pick_mw_k(int K) {
+  switch (K) {
+    case 1: return k_hist_mw<T, WT, 1>;
+    case 2: return k_hist_mw<T, WT, 2>;
+    case 3: return k_hist_mw<T, WT, 3>;
+    default: return k_hist_mw<T, WT, 0>;
+  }
+}
+
 template <typename T, int W, int MODE>
 XhkHistKernel pick_k(int K) {
   switch (K) {
@@ -1300,6 +1409,7 @@ XhkHistKernel pick_m(int K, int mode) {
     if (mode == 1) return pick_k<T, W, 1>(K);
     if (mode == 2) return pick_k<T, W, 2>(K);
     if (mode == 3) return pick_k<T, W, 3>(K);
+    if (mode == 5) { if constexpr (W == 3) return pick_k<T, W, 5>(K); else return pick_k<T, W, 1>(K); }
   }
   return pick_k<T, W, 0>(K);
 }
@@ -1346,4 +1456,5 @@ XhkColsKernel pick_cols_w(int w, int K) { return w == 0 ? pick_cols_k<T, 0>(K) :
     return w == 0 ? pick_m<T, 0>(K, mode) : w == 1 ? pick_m<T, 1>(K, mode) : pick_m<T, 2>(K, mode);     \
   }                                                                                                     \
   XhkWindowKernel xhk_pick_window_##DT(int K) { return pick_window_t<T>(K); }                           \
-  XhkColsKernel xhk_pick_cols_##DT(int w, int K) { return pick_cols_w<T>(w, K); }
+  XhkColsKernel xhk_pick_cols_##DT(int w, int K) { return pick_cols_w<T>(w, K); }                      \
+  XhkMwKernel xhk_pick_mw_##DT(int w, int K) { return w == 1 ? pick_mw_k<T, float>(K) : pick_mw_k<T, double>(K); }

@@ -115,6 +115,49 @@ class NcclCommunicator(Communicator):
         dist.broadcast_object_list(box, src=0)
         return cls(device, rank, world, box[0])
 
+    @classmethod
+    def from_env(cls, device: int = None, timeout: float = 120.0):
+        """Bootstrap without any other communication library (one node): ranks read ``RANK`` / ``WORLD_SIZE`` /
+        ``LOCAL_RANK`` (set by torchrun, mpirun wrappers, ...); rank 0 creates the NCCL id and publishes it through a file
+        that the other ranks wait for.  The file name is unique per launch (``XHIST_NCCL_ID_FILE``, or the launcher's pid —
+        the common parent of all ranks — and ``MASTER_PORT``)."""
+        import os
+        import tempfile
+        import time
+
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
+        if world == 1:
+            return cls(device, 0, 1, cls.create_unique_id())
+        path = os.environ.get("XHIST_NCCL_ID_FILE") or os.path.join(
+            tempfile.gettempdir(), f"xhist_b200_nccl_{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}.id")
+        if rank == 0:
+            uid = cls.create_unique_id()
+            tmp = path + f".{os.getpid()}"
+            with open(tmp, "wb") as f:
+                f.write(uid)
+            os.replace(tmp, path)                      # atomic: a reader sees nothing or all 128 bytes
+        else:
+            t0 = time.time()
+            while True:
+                try:
+                    with open(path, "rb") as f:
+                        uid = f.read()
+                    if len(uid) == _cabi.XH_NCCL_UNIQUE_ID_BYTES:
+                        break
+                except FileNotFoundError:
+                    pass
+                if time.time() - t0 > timeout:
+                    raise TimeoutError(f"rank {rank}: no NCCL id at {path} after {timeout} s")
+                time.sleep(0.01)
+        comm = cls(device, rank, world, uid)           # ncclCommInitRank returns once every rank has joined
+        if rank == 0:
+            try:
+                os.unlink(path)
+            except OSError:
+                pass
+        return comm
+
     def allreduce_device(self, ptr: int, count: int, is_f64: bool):
         _cabi.check(_cabi.lib().xh_comm_allreduce(self.device, ptr, count, 1 if is_f64 else 0), "xh_comm_allreduce")
 
@@ -129,7 +172,13 @@ class NcclCommunicator(Communicator):
         return out if is_f64 else out.view(np.int64)
 
     def allreduce_minmax(self, mn, mx):
-        raise NotImplementedError("pass explicit bin edges (or a range) with the NCCL communicator")
+        # every rank deposits (min, max) in its own slot of a zero vector; the sum is an all-gather (NaN stays NaN)
+        v = np.zeros(2 * self.world, dtype=np.float64)
+        v[2 * self.rank], v[2 * self.rank + 1] = mn, mx
+        v = self.allreduce_sum(v)
+        if np.isnan(v).any():
+            return float("nan"), float("nan")
+        return float(v[0::2].min()), float(v[1::2].max())
 
     def close(self):
         _cabi.check(_cabi.lib().xh_comm_destroy(self.device), "xh_comm_destroy")

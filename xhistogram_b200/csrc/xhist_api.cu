@@ -215,6 +215,10 @@ void build_lut(int k, XhkParams& p, const std::vector<T>& table, std::vector<uns
   int G = 64; while (G < 16 * nb && G < 8192) G <<= 1;
   std::vector<int> cnt;
   int steps = 0;
+  // how fine the table gets: until at most `target` edges lie within any 3 cells (or 8192 cells).  Measured on config 5
+  // (XH_LUT_STEPS = 4 / 3 / 2 / 1: 3.33 / 3.33 / 3.25 / 3.20 ms): fewer compare-and-advance steps per sample are worth more
+  // than the shared memory the larger table takes from the window
+  static const int target = [] { const char* e = std::getenv("XH_LUT_STEPS"); const int t = e ? std::atoi(e) : 1; return t >= 1 && t <= 4 ? t : 1; }();
   for (;; G <<= 1) {
     // keep the device's cell index within one cell of the exact one: G * (few ulp) must stay far below 1
     if (static_cast<long double>(G) * (sizeof(T) == 4 ? 6e-7L : 1e-15L) > 0.05L) { if (G > 64) G >>= 1; break; }
@@ -222,7 +226,7 @@ void build_lut(int k, XhkParams& p, const std::vector<T>& table, std::vector<uns
     for (int c = 0; c <= G; ++c) cnt[c] = std::max(1, count_le(c == G ? hi : lo + c * (hi - lo) / G));
     steps = 0;
     for (int c = 0; c < G; ++c) steps = std::max(steps, cnt[std::min(c + 2, G)] - cnt[std::max(c - 1, 0)]);
-    if (steps <= 4 || G >= 8192) break;
+    if (steps <= target || G >= 8192) break;
   }
   if (cnt.size() != static_cast<size_t>(G) + 1) {
     cnt.assign(G + 1, 0);
@@ -558,6 +562,12 @@ int find_verdict(Ctx* c, const PrepEntry& pe, const xh_desc* d, int tile_rows, l
       const unsigned long long cur = verdict_stats_host(c, i);
       if (v.samples_since > 0) {
         const double frac = static_cast<double>(cur - v.last_slow) / static_cast<double>(v.samples_since);
+        static const bool dbg = std::getenv("XH_DEBUG_VERDICT") != nullptr;
+        if (dbg) {
+          const XhkWindow* w = verdict_host(c, i);
+          std::fprintf(stderr, "[xh verdict %d] window lo=(%d,%d,%d) len=(%d,%d,%d) fx_mode=%d slow fraction %.4f (base %.4f) over %lld samples\n", i,
+                       w->lo[0], w->lo[1], w->lo[2], w->len[0], w->len[1], w->len[2], w->fx_mode, frac, v.base_frac, v.samples_since);
+        }
         if (v.base_frac < 0.0) v.base_frac = frac;
         else if (frac > 2.0 * v.base_frac + 0.02) { v.state = 0; v.base_frac = -1.0; }      // the data changed under the verdict: probe again
         v.last_slow = cur; v.samples_since = 0;

@@ -8,6 +8,15 @@
 #ifndef XH_CHEAP_SIDE_W3
 #define XH_CHEAP_SIDE_W3 0
 #endif
+#ifndef XH_PREFETCH_DIST
+#define XH_PREFETCH_DIST 2  // prefetch.global.L2 of the groups this many iterations ahead in the vector loops (0 = off).  The kernels
+                            // are latency-bound at 32 warps per SM (one 227 KB CTA) and every register is taken, so the extra
+                            // memory-level parallelism has to come without registers: measured on 1e9 samples, 0 / 2 / 4 iterations
+                            // ahead: weighted 2.254 / 1.992 / 2.032 ms, counts 1.369 / 1.250 / 1.254 ms
+#endif
+#ifndef XH_HALF_PIPE
+#define XH_HALF_PIPE 1      // big-record branch-free path: prefetch the next half group (A/B: make EXTRA=-DXH_HALF_PIPE=0)
+#endif
 
 
 namespace {
@@ -176,6 +185,8 @@ __device__ __forceinline__ void load4(const double* p, long long g, double (&v)[
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* q) { asm volatile("prefetch.global.L2 [%0];" ::"l"(q)); }
+
 // two samples (half a group) per load: big records are classified two samples at a time (see the MODE 2 half-group path)
 __device__ __forceinline__ void load2(const float* p, long long h, float (&v)[2]) {
   float2 q = __ldcs(reinterpret_cast<const float2*>(p) + h);
@@ -296,7 +307,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   // notice a cached probe verdict that no longer fits the data (xhist_api.cu, struct Verdict).
   unsigned nslow = 0;      // per thread; summed into s_slow at the end (a shared counter bumped per spill serialises the
                            // lanes of a warp on one address: data that spills a lot — uniform over the bins — ran 4x slower)
+#ifdef XH_NO_STATS
+  auto note_slow = [&]() { };
+#else
   auto note_slow = [&]() { ++nslow; };
+#endif
   auto spill_add = [&](OT* out_row, long long gbin, double wv) { global_add(out_row, gbin, wv); note_slow(); };
   // general path of one sample: exact bins, then shared window / global spill / drop.
   // Returns the window bin when the caller should do the shared add itself, else -1.
@@ -487,6 +502,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) load4(px[k] + head, gu, xv[u][k]);
           }
+#if XH_PREFETCH_DIST > 0
+          const long long gp = gu + static_cast<long long>(XH_PREFETCH_DIST * U) * nthr;
+          if (gp < nvec) {
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) prefetch_l2(px[k] + head + 4 * gp);
+          }
+#endif
         };
 #pragma unroll
         for (int u = 0; u < U; ++u) load_slot(u, tid + static_cast<long long>(u) * nthr);
@@ -540,11 +562,40 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
         // its time in divergent search loops (267 instructions per sample, 75 % issue-bound: profiles/r2_ncu_cfg5.md).
         // Non-uniform variable: table entry of cell c-1 = a bin at or below the sample's, then lut_steps
         // compare-and-advance steps; window spills leave as inline predicated global REDs.
-        for (long long g = tid; g < 2 * nvec; g += nthr) {          // g counts half groups
-          T xh[KMAX][2]; WT wh[2] = {WT(1), WT(1)};
+        // software pipeline: the loads of the next half group are issued before the current one is classified (one
+        // 16-byte load per array and thread in flight was latency-bound: 30 % of the stall samples at the loads)
+        T xn[KMAX][2]; WT wn[2] = {WT(1), WT(1)};
+        auto fetch = [&](long long gg) {
+          if (gg < 2 * nvec) {
 #pragma unroll
-          for (int k = 0; k < KMAX; ++k) load2(px[k] + head, g, xh[k]);
-          if constexpr (W != 0) load2(pw + head, g, wh);
+            for (int k = 0; k < KMAX; ++k) load2(px[k] + head, gg, xn[k]);
+            if constexpr (W != 0) load2(pw + head, gg, wn);
+          }
+        };
+#if XH_HALF_PIPE
+        fetch(tid);
+#endif
+        for (long long g = tid; g < 2 * nvec; g += nthr) {          // g counts half groups
+          T xh[KMAX][2]; WT wh[2];
+#if !XH_HALF_PIPE
+          fetch(g);
+#endif
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) { xh[k][0] = xn[k][0]; xh[k][1] = xn[k][1]; }
+          wh[0] = wn[0]; wh[1] = wn[1];
+#if XH_HALF_PIPE
+          fetch(g + nthr);
+#endif
+#if XH_PREFETCH_DIST > 0
+          {
+            const long long gp = g + static_cast<long long>(XH_PREFETCH_DIST + 1) * nthr;      // half groups ahead of the register prefetch
+            if (gp < 2 * nvec) {
+#pragma unroll
+              for (int k = 0; k < KMAX; ++k) prefetch_l2(px[k] + head + 2 * gp);
+              if constexpr (W != 0) prefetch_l2(pw + head + 2 * gp);
+            }
+          }
+#endif
           int jb[KMAX][2]; bool okr[2] = {true, true}, cert[2] = {true, true};
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) {
@@ -606,6 +657,20 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       for (long long g = first_group(); group_ok(g); g = next_group(g)) {
         T xv[U][KMAX][4];
         WT wv[U][4];
+#if XH_PREFETCH_DIST > 0
+        {        // pull the lines of a later iteration into L2 (no registers held, unlike a register prefetch); with dynamic
+                 // dealing some warp of the CTA will draw these groups about that many iterations from now
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const long long gp = g + static_cast<long long>(XH_PREFETCH_DIST * U) * nthr + static_cast<long long>(u) * ustride;
+            if (gp < nvec) {
+#pragma unroll
+              for (int k = 0; k < KMAX; ++k) prefetch_l2(px[k] + head + 4 * gp);
+              if constexpr (W != 0) prefetch_l2(pw + head + 4 * gp);
+            }
+          }
+        }
+#endif
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const long long gu = g + static_cast<long long>(u) * ustride;

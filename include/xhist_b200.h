@@ -51,6 +51,7 @@ typedef enum xh_mem { XH_HOST = 0, XH_DEVICE = 1 } xh_mem;
 #define XH_FLAG_FORCE_GLOBAL 2u /* testing: bypass the shared-memory histogram, global atomics only         */
 #define XH_FLAG_FORCE_SEARCH 4u /* testing: bypass the uniform-edge fast path, binary search only           */
 #define XH_FLAG_FORCE_WINDOW 8u /* testing: use the windowed shared-memory histogram even if all bins fit   */
+#define XH_FLAG_FORCE_PACKED 512u /* testing: counts take the packed 16-bit shared histogram whenever it applies            */
 #define XH_FLAG_NO_FX32 16u     /* testing: fp32 weights never take the one-limb (4 bytes per bin) accumulation  */
 #define XH_FLAG_ALLREDUCE 64u   /* sum the (n_rows, bins) result over the ranks of this device's communicator
                                    (xh_comm_init_rank) with ncclAllReduce before the density / the copy to `out`:

@@ -18,6 +18,7 @@ PATHS = {
     "windowed": _cabi.XH_FLAG_FORCE_WINDOW,
     "windowed_search": _cabi.XH_FLAG_FORCE_WINDOW | _cabi.XH_FLAG_FORCE_SEARCH,
     "no_fx32": _cabi.XH_FLAG_NO_FX32,
+    "packed_counts": _cabi.XH_FLAG_FORCE_PACKED,
 }
 
 
@@ -69,7 +70,7 @@ def _random_problem(seed):
 def test_random_problems_match_oracle(seed):
     args, edges, w = _random_problem(seed)
     want = O.block_bincount(args, edges, w)
-    for path in ("default", "windowed", "global_atomics"):
+    for path in ("default", "windowed", "global_atomics", "packed_counts"):
         with core.debug_flags(PATHS[path]):
             h, _ = core.histogram(*args, bins=edges, axis=-1, weights=w)
         assert_hist_equal(h, want, rtol=1e-6)

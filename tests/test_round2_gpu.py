@@ -294,3 +294,38 @@ def test_list_of_weights_weighted_mean_of_the_tutorial():
     num, _ = O.histogram(a, bins=e, weights=vol * t)
     den, _ = O.histogram(a, bins=e, weights=vol)
     np.testing.assert_allclose(h[0] / h[1], num / den, rtol=1e-9)
+
+
+def test_packed_counts_take_over_when_the_window_spills():
+    """Counts over 256 x 256 bins with data spread over all of them: the windowed launch spills 12 %, the library notices
+    (slow-path counter of the cached verdict) and later calls use the packed 16-bit histogram; every call is bit-exact."""
+    n = 6_000_000
+    r = np.random.default_rng(60)
+    x, y = r.random(n).astype(np.float32), r.random(n).astype(np.float32)
+    e = np.linspace(0, 1, 257)
+    want, _ = O.histogram(x, y, bins=[e, e], threads=8)
+    dx, dy = DeviceArray.from_numpy(x), DeviceArray.from_numpy(y)
+    for _ in range(8):
+        assert np.array_equal(core.histogram(dx, dy, bins=[e, e])[0], want)
+    with core.debug_flags(_cabi.XH_FLAG_FORCE_PACKED):
+        assert np.array_equal(core.histogram(dx, dy, bins=[e, e])[0], want)
+        assert np.array_equal(core.histogram(x, y, bins=[e, e])[0], want)                 # host pipeline
+
+
+@pytest.mark.parametrize("layout", ["flat", "rows"])
+def test_packed_counts_guard_bit_carries(layout):
+    """All samples in very few bins: the 16-bit fields reach 2^15 thousands of times (and both fields of one word are hot)."""
+    n = 40_000_000
+    x = np.zeros(n, dtype=np.float32)
+    x[1::2] = 0.03                                   # two neighbouring bins that share a shared-memory word
+    x[::1001] = 7.9
+    y = np.full(n, 0.5, dtype=np.float32)
+    e = np.linspace(-8, 8, 513)                      # 512 x 200 bins: does not fit as 4-byte bins
+    e2 = np.linspace(0, 1, 201)
+    if layout == "rows":
+        x, y = x.reshape(4, -1), y.reshape(4, -1)
+    axis = 1 if layout == "rows" else None
+    want, _ = O.histogram(x, y, bins=[e, e2], axis=axis, threads=8)
+    with core.debug_flags(_cabi.XH_FLAG_FORCE_PACKED):
+        got, _ = core.histogram(x, y, bins=[e, e2], axis=axis)
+    assert np.array_equal(got, want)

@@ -453,7 +453,7 @@ unsigned long long verdict_stats_host(Ctx* c, int slot) { return *reinterpret_ca
 // Launch plan of one block whose data/weights/out pointers are DEVICE pointers.
 // fx32 = true plans the k_hist<W = 3> sibling of an fp32-weighted block (4 bytes per shared bin instead of 8).
 int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Plan& pl, int tile_rows = 1, long long tile_n = 0,
-               bool fx32 = false) {
+               bool fx32 = false, bool packed = false) {
   XhkParams& p = pl.p;
   p = pr.base;
   p.tile_rows = tile_rows; p.tile_n = static_cast<int>(tile_n); p.tile_magic = 1; p.tile_shift = 0;
@@ -477,6 +477,30 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
 
   // shared-memory budget
   const size_t edges_al = pr.edges_al;
+  if (packed) {
+    // counts packed two to a shared word (k_hist<W = 4>): the whole bin space, half the bytes; only planned when it fits
+    const long long budget = static_cast<long long>(c->smem_optin) - XHK_STATIC_SMEM - static_cast<long long>(pr.edges_al);
+    const size_t smem_pk = pr.edges_al + (static_cast<size_t>((B + 1) / 2) + 32) * 4;
+    if (static_cast<long long>(smem_pk) > budget + static_cast<long long>(pr.edges_al)) return fail(XH_ERR_UNSUPPORTED, "packed counts do not fit");
+    p.hist_mode = XHK_FULL; p.hist_capacity = static_cast<int>(B);
+    const long long total = p.M * p.N;
+    int grid = c->sm_count;
+    const long long min_per_cta = 4096;
+    if (total < static_cast<long long>(grid) * min_per_cta) grid = static_cast<int>(std::max<long long>(1, (total + min_per_cta - 1) / min_per_cta));
+    if (p.M >= 16ll * grid) p.partition = XHK_PART_ROWS;
+    else {
+      p.partition = XHK_PART_SAMPLES;
+      long long per = (total + grid - 1) / grid;
+      per = (per + 1023) / 1024 * 1024;
+      p.per_cta = per;
+      grid = static_cast<int>((total + per - 1) / per);
+    }
+    p.fx_vbits = 24; p.w_dtype = XH_NONE; p.store_owned_rows = 0;
+    pl.need_window = false;
+    pl.zero = (d->flags & XH_FLAG_NO_ZERO) ? Plan::ZERO_NONE : Plan::ZERO_ALL;
+    pl.l.dtype = d->dtype; pl.l.w_dtype = 4; pl.l.grid = grid; pl.l.threads = XHK_THREADS; pl.l.smem_bytes = smem_pk; pl.l.stream = stream;
+    return XH_OK;
+  }
   const size_t item = (d->w_dtype == XH_NONE || fx32) ? 4 : 8;
   const long long budget1 = static_cast<long long>(c->smem_optin) - XHK_STATIC_SMEM - static_cast<long long>(edges_al);  // 1 CTA / SM
   if (budget1 < 0) return fail(XH_ERR_UNSUPPORTED, "bin edges (%zu bytes) do not fit in shared memory", pr.edge_host.size());
@@ -614,6 +638,10 @@ int enqueue(Ctx* c, const PrepEntry& pe, const xh_desc* d, Plan& pl, Plan* sib, 
       if (sib) sib->p.window = c->window;
     }
   }
+  if (ready && slot >= 0 && c->verdicts[slot].base_frac > 0.02) {        // data that spills a lot: see kernel_mode()
+    pl.p.spilly = 1;
+    if (sib) sib->p.spilly = 1;
+  }
   Plan* run_main = &pl; Plan* run_sib = sib;
   if (ready && sib) {                       // the host knows which form the probe chose
     if (verdict_host(c, slot)->fx_mode == 32) { run_main = nullptr; }
@@ -661,12 +689,33 @@ int enqueue(Ctx* c, const PrepEntry& pe, const xh_desc* d, Plan& pl, Plan* sib, 
   return XH_OK;
 }
 
+// Slow-path fraction recorded for the cached verdict of this block, or -1 when there is none yet.
+double verdict_slow_fraction(Ctx* c, const PrepEntry& pe, const xh_desc* d, int tile_rows, long long tile_n, int budget, int budget32) {
+  for (int i = 0; i < kVerdictSlots; ++i) {
+    const Verdict& v = c->verdicts[i];
+    if (verdict_matches(v, pe, d, tile_rows, tile_n, budget, budget32) && v.state == 2) return v.base_frac;
+  }
+  return -1.0;
+}
+
 // Plan a block and, for fp32 weights, its fx32 sibling; enqueue.
 int plan_and_enqueue(Ctx* c, const PrepEntry& pe, const xh_desc* d, cudaStream_t stream, bool cache, int tile_rows = 1, long long tile_n = 0) {
   const Prep& pr = pe.pr;
   Plan pl;
   int rc = plan_block(c, pr, d, stream, pl, tile_rows, tile_n);
   if (rc) return rc;
+  // Counts whose bin space does not fit as 4-byte bins but fits as packed 16-bit fields: when the windowed launch was seen to
+  // spill (the data is spread over more bins than the window holds), later calls use the packed form — everything in shared
+  // memory, no spills.  For data the window holds (spill fraction below 2 %) the windowed form stays: its non-returning
+  // shared adds are cheaper than the packed form's returning ones.
+  const bool forced = (d->flags & XH_FLAG_FORCE_PACKED) != 0;
+  if (d->w_dtype == XH_NONE && d->dtype != XH_I64 && pr.base.all_uniform && tile_rows == 1 && (pl.p.hist_mode == XHK_WINDOW || forced) &&
+      !(d->flags & (XH_FLAG_FORCE_GLOBAL | XH_FLAG_FORCE_WINDOW | XH_FLAG_FORCE_SEARCH))) {
+    if (forced || (cache && verdict_slow_fraction(c, pe, d, tile_rows, tile_n, pl.window_budget, 0) > 0.02)) {
+      Plan pk;
+      if (plan_block(c, pr, d, stream, pk, tile_rows, tile_n, false, true) == XH_OK) return enqueue(c, pe, d, pk, nullptr, false, tile_rows, tile_n);
+    }
+  }
   Plan sib;
   // The one-limb form pays off through its larger window, i.e. when the 8-byte bins do not all fit; when they do,
   // the two-limb form has no spills and no wraps.  Wraps reach the output through global adds, so the sibling

@@ -308,7 +308,9 @@ int kernel_mode(const XhkParams& p, int dtype, int w = 0) {
   if (p.all_uniform) {
     if (p.tile_rows > 1) return 3;                       // row tiling is a compile-time variant of the fast kernel
     // one-limb weights over a short per-CTA range: dynamic dealing of the groups to the warps (see k_hist, MODE 5)
-    if (w == 3 && p.partition == XHK_PART_SAMPLES && p.per_cta <= (5ll << 19)) return 5;
+    // (also for data that spills a lot: warps that run long side loops no longer hold up their CTA — uniform data on config 3:
+    //  4.9 -> 3.5 ms per 1e9 samples)
+    if (w == 3 && p.partition == XHK_PART_SAMPLES && (p.per_cta <= (5ll << 19) || p.spilly)) return 5;
     return 1;
   }
   return (p.all_branch_free && p.n_vars <= 4) ? 2 : 0;
@@ -319,6 +321,11 @@ int kernel_mode(const XhkParams& p, int dtype, int w = 0) {
 
 
 cudaError_t xhk_set_smem_limits(int max_optin) {
+  for (int dt = 1; dt <= 2; ++dt)
+    for (int k = 1; k <= 4; ++k) {
+      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick(dt, 4, k, 1)), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+      if (e != cudaSuccess) return e;
+    }
   for (int dt = 1; dt <= 3; ++dt)
     for (int w = 0; w <= (dt == 3 ? 2 : 3); ++w)
       for (int k = 1; k <= 5; ++k)
@@ -381,7 +388,7 @@ cudaError_t xhk_launch_window(const XhkParams& p, const XhkLaunch& l, XhkWindow*
 }
 
 cudaError_t xhk_launch_zero_shared_rows(const XhkParams& p, const XhkLaunch& l) {
-  if (l.w_dtype == 0) k_zero_shared_rows<unsigned long long><<<l.grid, 256, 0, l.stream>>>(p, l.grid);
+  if (l.w_dtype == 0 || l.w_dtype == 4) k_zero_shared_rows<unsigned long long><<<l.grid, 256, 0, l.stream>>>(p, l.grid);
   else k_zero_shared_rows<double><<<l.grid, 256, 0, l.stream>>>(p, l.grid);
   return cudaGetLastError();
 }

@@ -95,6 +95,7 @@ struct XhkParams {
   int tile_n;                       // samples of one real row
   unsigned tile_magic; int tile_shift;   // q = (umulhi(n, magic) + n) >> shift == n / tile_n for n < 2^31
   int fx_vbits;                     // fixed point: |v| < 2^fx_vbits keeps every per-flush bin sum below 2^63
+  int spilly;                       // host hint from the cached verdict: > 2 % of the samples left the fast path last time
   unsigned long long* stats;        // device counter: samples that left the fast path (window spills, weights outside the
                                     // fixed-point form) — lets the host notice a cached probe verdict that no longer fits
   int fx32_sibling;                 // 1: a k_hist<W = 3> launch of the same block precedes this one and does the work
@@ -103,7 +104,7 @@ struct XhkParams {
 
 struct XhkLaunch {
   int dtype;       // 1 f32, 2 f64, 3 int64 (xh_dtype)
-  int w_dtype;     // 0 none, 1 f32, 2 f64, 3 f32 accumulated in one u32 limb per bin (fx32 sibling)
+  int w_dtype;     // 0 none, 1 f32, 2 f64, 3 f32 accumulated in one u32 limb per bin (fx32 sibling), 4 none + counts packed as 16-bit fields
   int grid, threads;
   size_t smem_bytes;
   cudaStream_t stream;

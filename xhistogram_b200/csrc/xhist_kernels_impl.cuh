@@ -219,8 +219,10 @@ template <typename T, int W, int KT, int MODE>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__ XhkParams p) {
   constexpr bool FAST = (MODE == 1 || MODE == 3 || MODE == 5);   // 3: the same with row tiling compiled in (1: compiled out);
                                                                   // 5: mode 1 with dynamic dealing of the groups to the warps (W = 3 only)
-  using HT = typename std::conditional<W == 0 || W == 3, unsigned int, double>::type;   // shared accumulator
-  using OT = typename std::conditional<W == 0, unsigned long long, double>::type;       // global accumulator
+  constexpr bool CNT = (W == 0 || W == 4);    // counts (no weights)
+  constexpr bool PK = (W == 4);               // counts packed two to a shared word (16-bit fields with a guard bit, see shared_add1)
+  using HT = typename std::conditional<CNT || W == 3, unsigned int, double>::type;   // shared accumulator
+  using OT = typename std::conditional<CNT, unsigned long long, double>::type;       // global accumulator
   using WT = typename WType<W>::type;
   constexpr int KMAX = KT ? KT : XHK_MAX_VARS;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -268,13 +270,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   // obtained for free by seeding the Horner evaluation of the joint bin with the local row
   const bool tiled = (MODE == 3) || (MODE != 1 && MODE != 5 && p.tile_rows > 1);
   wtot *= p.tile_rows;
-  const int hwords = (wtot + 32) * static_cast<int>(sizeof(HT) / 4);               // (+ the trash slots)
+  const int hwords = PK ? ((wtot + 1) / 2 + 32) : (wtot + 32) * static_cast<int>(sizeof(HT) / 4);   // (+ the trash slots)
   for (int i = tid; i < hwords; i += nthr) hregion[i] = 0u;
   // weighted accumulation mode (uniform for the launch): exact fixed point in two u32 limbs, or float64 adds
   // `fx` can fall back to float64 adds for one row segment (see s_redo), hence not const
   bool fx = false, fx_launch = false; WT fx_mul = WT(0), fx_limit = WT(0); double fx_unmul = 0.0, fx_carry = 0.0;
   bool owned = false;      // the current row segment is a whole row that only this CTA touches: flushed with plain stores
-  if constexpr (W != 0) {
+  if constexpr (!CNT) {
     if (p.hist_mode != XHK_GLOBAL && p.window->fx_ok) {
       fx = fx_launch = true; fx_mul = static_cast<WT>(p.window->fx_mul); fx_limit = static_cast<WT>(p.window->fx_limit); fx_unmul = p.window->fx_unmul;
       fx_carry = 4294967296.0 * fx_unmul;   // fx32: what one wrap of the u32 limb is worth
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 
   // ---- accumulation primitives ------------------------------------------------------------
   auto global_add = [&](OT* out_row, long long gbin, double wv) {
-    if constexpr (W == 0) atomicAdd(out_row + gbin, 1ull); else atomicAdd(out_row + gbin, wv);
+    if constexpr (CNT) atomicAdd(out_row + gbin, 1ull); else atomicAdd(out_row + gbin, wv);
   };
   // an in-range sample that the shared histogram could not take (outside the window, or a weight outside the
   // fixed-point form): global add + one tick of the CTA's slow-path counter.  The host watches the counter to
@@ -355,7 +357,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   //             Otherwise float64 adds in shared memory (red.shared.add.f64 = LDS + DADD + ATOMS.CAST.SPIN loop;
   //             an explicit atomicCAS loop compiles to plain ATOMS.CAS.64 and measured >4x slower on B200).
   auto shared_add1 = [&](int wbin, WT w, OT* out_row) {
-    if constexpr (W == 0) {
+    if constexpr (PK) {
+      // Packed counts: bin b lives in the 16-bit field (b & 1) of word b >> 1.  A field never passes 2^15 + (adds in flight):
+      // the add that finds the field at 2^15 - 1 (ATOMS returns the old word) takes 2^15 out of the field again and
+      // credits it to the output, so no field ever carries into its neighbour.  65 536 bins cost 128 KB instead of 256 KB
+      // — the whole bin space of config 3 fits, no window, no spills, whatever the distribution of the data.
+      const unsigned sh = (static_cast<unsigned>(wbin) & 1u) * 16u;
+      const unsigned addr = sh_lo + 4u * (static_cast<unsigned>(wbin) >> 1);
+      const unsigned old = atoms_add_u32(addr, 1u << sh);
+      if (((old >> sh) & 0xFFFFu) == 0x7FFFu) {
+        reds_add_u32(addr, 0u - (0x8000u << sh));
+        atomicAdd(out_row + window_to_global(wbin), 0x8000ull);
+      }
+    } else if constexpr (CNT) {
       reds_add_u32(sh_lo + 4u * static_cast<unsigned>(wbin), 1u);
     } else if constexpr (W == 3) {
       // fx32: v = w * 2^s as ONE u32 limb.  The returned old value tells when the limb wraps; a wrap is worth
@@ -435,13 +449,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
       px[k] = (k < K) ? static_cast<const T*>(p.data[k]) + r * p.stride[k] + c0 : nullptr;
-    const WT* pw = (W != 0) ? static_cast<const WT*>(p.w) + r * p.wstride + c0 : nullptr;
+    const WT* pw = (!CNT) ? static_cast<const WT*>(p.w) + r * p.wstride + c0 : nullptr;
     long long head = ((16 - (reinterpret_cast<uintptr_t>(px[0]) & 15)) & 15) / sizeof(T);
     if (head > len) head = len;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
       if (k < K) vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(px[k] + head) & 15) == 0);
-    if (W != 0) vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(pw + head) & 15) == 0);
+    if (!CNT) vec_ok = vec_ok && ((reinterpret_cast<uintptr_t>(pw + head) & 15) == 0);
     if (!vec_ok) head = len;
     const long long nvec = (len - head) >> 2;  // groups of 4 samples
     const long long tail0 = head + (nvec << 2);
@@ -458,7 +472,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) x[k] = (k < K) ? px[k][i] : T(0);
       WT wv[4] = {WT(1), WT(1), WT(1), WT(1)};
-      if constexpr (W != 0) wv[0] = pw[i];
+      if constexpr (!CNT) wv[0] = pw[i];
       const int wbin = general_sample(x, static_cast<double>(wv[0]), out_row, local_row(i));
       if (wbin >= 0) shared_add1(wbin, wv[0], out_row);
     };
@@ -467,8 +481,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 
     if constexpr (KT != 0) {
       // vector body: 4 samples per 16-byte load, U loads in flight per array and thread
-      constexpr int REC = static_cast<int>(sizeof(T)) * KMAX + (W == 0 ? 0 : static_cast<int>(sizeof(WT)));   // bytes per sample
-      constexpr int U = (FAST && W == 0 && REC <= 8) ? 3 : (REC <= 12) ? 2 : 1;
+      constexpr int REC = static_cast<int>(sizeof(T)) * KMAX + (CNT ? 0 : static_cast<int>(sizeof(WT)));   // bytes per sample
+      constexpr int U = (FAST && CNT && REC <= 8) ? 3 : (REC <= 12) ? 2 : 1;
       const float fx_mulp = pin(static_cast<float>(fx_mul) * 2.98023223876953125e-8f);   // fx32: fx_mul * 2^-25
       int jbias[KMAX];          // fused fast path: window offset of the bin number + RoundSplit::kBias
 #pragma unroll
@@ -489,7 +503,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       auto first_group = [&]() -> long long { if constexpr (DYN) return draw(); else return tid; };
       auto next_group = [&](long long g) -> long long { if constexpr (DYN) return draw(); else return g + static_cast<long long>(U) * nthr; };
       auto group_ok = [&](long long g) -> bool { if constexpr (DYN) return g - (tid & 31) < nvec; else return g < nvec; };   // (warp-uniform when dynamic)
-      if constexpr (FAST && W == 0) {
+      if constexpr (FAST && CNT) {
         // ---- counts on the fast path: fused classify + RED, software-pipelined over U register slots of 4 samples
         // per array — a slot is refilled with the group U steps ahead as soon as it has been consumed, so a warp keeps
         // loads in flight while it computes (measured +3-4 % on configs 2 / 3-counts / 4; the same order measured
@@ -533,8 +547,31 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
               }
               idx[e] = good ? static_cast<unsigned>(wbin) : trash;
             }
+            if constexpr (PK) {
+              unsigned old[4], shf[4], wad[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) reds_add_u32(sh_lo + 4u * idx[e], 1u);
+              for (int e = 0; e < 4; ++e) {
+                const bool good = static_cast<int>(idx[e]) >= 0;
+                shf[e] = (idx[e] & 1u) * 16u;
+                wad[e] = sh_lo + 4u * (good ? (idx[e] >> 1) : idx[e]);       // (a trash slot keeps its own word)
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) old[e] = atoms_add_u32(wad[e], 1u << shf[e]);
+              unsigned full15 = 0;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) full15 |= ((((old[e] >> shf[e]) & 0xFFFFu) == 0x7FFFu) && static_cast<int>(idx[e]) >= 0) ? (1u << e) : 0u;
+              if (full15) {           // rare: once per 2^15 adds to one bin
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (full15 & (1u << e)) {
+                    reds_add_u32(wad[e], 0u - (0x8000u << shf[e]));
+                    atomicAdd(out_row + window_to_global(static_cast<int>(idx[e])), 0x8000ull);
+                  }
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) reds_add_u32(sh_lo + 4u * idx[e], 1u);
+            }
             if (live && max(max(idx[0], idx[1]), max(idx[2], idx[3])) >= 0x80000000u) {
               unsigned side = 0;
 #pragma unroll
@@ -569,7 +606,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
           if (gg < 2 * nvec) {
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) load2(px[k] + head, gg, xn[k]);
-            if constexpr (W != 0) load2(pw + head, gg, wn);
+            if constexpr (!CNT) load2(pw + head, gg, wn);
           }
         };
 #if XH_HALF_PIPE
@@ -592,7 +629,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             if (gp < 2 * nvec) {
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) prefetch_l2(px[k] + head + 2 * gp);
-              if constexpr (W != 0) prefetch_l2(pw + head + 2 * gp);
+              if constexpr (!CNT) prefetch_l2(pw + head + 2 * gp);
             }
           }
 #endif
@@ -666,7 +703,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             if (gp < nvec) {
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) prefetch_l2(px[k] + head + 4 * gp);
-              if constexpr (W != 0) prefetch_l2(pw + head + 4 * gp);
+              if constexpr (!CNT) prefetch_l2(pw + head + 4 * gp);
             }
           }
         }
@@ -677,9 +714,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
           if (gu < nvec) {
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) load4(px[k] + head, gu, xv[u][k]);
-            if constexpr (W != 0) load4(pw + head, gu, wv[u]);
+            if constexpr (!CNT) load4(pw + head, gu, wv[u]);
           }
-          if constexpr (W == 0) { wv[u][0] = wv[u][1] = wv[u][2] = wv[u][3] = WT(1); }
+          if constexpr (CNT) { wv[u][0] = wv[u][1] = wv[u][2] = wv[u][3] = WT(1); }
         }
         int wb[U][4];
         if constexpr (MODE == 2) {
@@ -739,7 +776,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
               const bool good = cert[e] & okr[e];
               wb[u][e] = (good & inwin) ? wbin : -1;
               if (good & !inwin) {                      // in range, outside the shared window: one global RED
-                if constexpr (W == 0) atomicAdd(out_row + gbin, 1ull);
+                if constexpr (CNT) atomicAdd(out_row + gbin, 1ull);
                 else atomicAdd(out_row + gbin, static_cast<double>(wv[u][e]));
                 ++nslow;
               }
@@ -966,7 +1003,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
               }
             }
           }
-        } else if (W != 0 && fx) {
+        } else if (!CNT && fx) {
           // fixed-point shared adds, straight-line: 4 low-limb ATOMS back to back, then the 4 high-limb REDs
           // (each takes the carry from the value its ATOMS returned)
           unsigned inexact = 0;
@@ -1027,7 +1064,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
       // value of shared bin b (cleared on the way out)
       auto take = [&](int b, bool& nz) -> OT {
         OT v;
-        if constexpr (W == 0) { v = static_cast<OT>(shist[b]); nz = v != 0; shist[b] = 0u; }
+        if constexpr (CNT) { v = static_cast<OT>(shist[b]); nz = v != 0; shist[b] = 0u; }
         else if constexpr (W == 3) { const unsigned q = lo32[b]; nz = q != 0u; v = static_cast<double>(q) * fx_unmul; lo32[b] = 0u; }
         else if (fx) {
           const long long iv = static_cast<long long>((static_cast<unsigned long long>(hi32[b]) << 32) | lo32[b]);
@@ -1037,6 +1074,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
         return v;
       };
       const int L = (K > 0) ? wlen[K - 1] : 1;          // bins of the last variable inside the window: contiguous in `out`
+      if constexpr (PK) {
+        // packed counts: one thread takes a whole word (two bins), so clearing needs no atomics
+        for (int i = tid; i < (wtot + 1) / 2; i += nthr) {
+          const unsigned q = lo32[i];
+          lo32[i] = 0u;
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const int b = 2 * i + hlf;
+            const unsigned long long v = (q >> (16 * hlf)) & 0xFFFFu;
+            if (b < wtot && v) atomicAdd(out_row + (full ? static_cast<long long>(b) : window_to_global(b)), v);
+          }
+        }
+      } else
       if (owned) {
         for (int b = tid; b < wtot; b += nthr) { bool nz; const OT v = take(b, nz); out_row[b] = v; }
       } else if (!full && L >= 32) {
@@ -1480,6 +1530,13 @@ XhkHistKernel pick_m(int K, int mode) {
 }
 
 
+// packed counts (W = 4): fused fast path only (every variable uniform, no row tiling), floating-point data
+template <typename T>
+XhkHistKernel pick_pk(int K) {
+  if constexpr (std::is_floating_point<T>::value) return pick_k<T, 4, 1>(K);
+  else return nullptr;
+}
+
 // fx32 sibling (W = 3): floating-point data only (the host never asks for it with int64 data)
 template <typename T>
 XhkHistKernel pick_fx32(int K, int mode) {
@@ -1518,6 +1575,7 @@ XhkColsKernel pick_cols_w(int w, int K) { return w == 0 ? pick_cols_k<T, 0>(K) :
   XhkHistKernel xhk_pick_hist_##DT(int w, int K, int mode) {                                           \
     if (!(ALLOW_FAST)) mode = 0;                                                                        \
     if (w == 3) return pick_fx32<T>(K, mode);                                                           \
+    if (w == 4) return pick_pk<T>(K);                                                                   \
     return w == 0 ? pick_m<T, 0>(K, mode) : w == 1 ? pick_m<T, 1>(K, mode) : pick_m<T, 2>(K, mode);     \
   }                                                                                                     \
   XhkWindowKernel xhk_pick_window_##DT(int K) { return pick_window_t<T>(K); }                           \

@@ -343,8 +343,15 @@ def main():
             _cabi.check(lib.xh_timer_start(dev), "timer")
             t0 = time.perf_counter()
             last = None
+            trace = [] if os.environ.get("XH_BENCH_TRACE") else None
             for _ in range(steps):
+                if trace is not None:
+                    ts = time.perf_counter()
                 last = fn()
+                if trace is not None:
+                    trace.append(round((time.perf_counter() - ts) * 1e3, 3))
+            if trace is not None:
+                print(f"[trace rank {rank}] {getattr(fn, '__name__', 'step')}: {trace}", file=sys.stderr, flush=True)
             ms = _cabi.C.c_float(0)
             _cabi.check(lib.xh_timer_stop(dev, _cabi.C.byref(ms)), "timer")      # synchronises the library stream
             wall_ms = (time.perf_counter() - t0) * 1e3

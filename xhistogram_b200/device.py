@@ -176,13 +176,23 @@ class ResultPool:
         if lst:
             ptr = lst.pop()
         else:
-            if self.total + cap > self.limit:
+            # page-locking is slow (about 10 ms for 2 MB): the first miss of a size class takes a few blocks at once, so that a
+            # caller who keeps the previous result while asking for the next one does not pay it again in steady state
+            ptr = None
+            for _ in range(1 if cap in self.free else 3):
+                if self.total + cap > self.limit:
+                    break
+                p = C.c_void_p()
+                if _cabi.lib().xh_host_alloc(cap, C.byref(p)) != 0:
+                    break
+                self.total += cap
+                if ptr is None:
+                    ptr = p.value
+                else:
+                    self.free.setdefault(cap, []).append(p.value)
+            self.free.setdefault(cap, [])
+            if ptr is None:
                 return None
-            p = C.c_void_p()
-            if _cabi.lib().xh_host_alloc(cap, C.byref(p)) != 0:
-                return None
-            ptr = p.value
-            self.total += cap
         return np.asarray(_ResultBlock(self, ptr, cap, tuple(shape), dtype.str))
 
     def _give(self, ptr, cap):

@@ -24,7 +24,7 @@ win = [v for n, v in launches if n.startswith("k_window")]
 if big:
     kb = sum(big) / len(big)
     kd = (sum(dens) / len(dens)) if dens else 0.0
-    out += ["", f"Device-resident step (2.5e8 samples): `k_hist<float, 3, 2, 1>` {kb / 1e6:.3f} ms per launch ({len(big)} launches) + `k_density_small` "
+    out += ["", f"Device-resident step (2.5e8 samples): `k_hist<float, 3, 2, 5>` (the one-limb weighted kernel; MODE 5 = dynamic dealing, chosen for per-CTA ranges this short) {kb / 1e6:.3f} ms per launch ({len(big)} launches) + `k_density_small` "
             f"{kd / 1e3:.1f} us -> `k_hist` is {100 * kb / (kb + kd):.1f}% of the step's kernel time (bench.py's roofline divides the algorithmic bytes by the "
             "CUDA-event time of both together).",
             f"`k_window` runs {len(win)} times in the whole run: once per new (edge tables, buffers, shape) key and once per staged 8M-sample chunk of the "

@@ -14,9 +14,7 @@
                             // memory-level parallelism has to come without registers: measured on 1e9 samples, 0 / 2 / 4 iterations
                             // ahead: weighted 2.254 / 1.992 / 2.032 ms, counts 1.369 / 1.250 / 1.254 ms
 #endif
-#ifndef XH_HALF_PIPE
-#define XH_HALF_PIPE 1      // big-record branch-free path: prefetch the next half group (A/B: make EXTRA=-DXH_HALF_PIPE=0)
-#endif
+
 
 
 namespace {
@@ -309,11 +307,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
   // notice a cached probe verdict that no longer fits the data (xhist_api.cu, struct Verdict).
   unsigned nslow = 0;      // per thread; summed into s_slow at the end (a shared counter bumped per spill serialises the
                            // lanes of a warp on one address: data that spills a lot — uniform over the bins — ran 4x slower)
-#ifdef XH_NO_STATS
-  auto note_slow = [&]() { };
-#else
   auto note_slow = [&]() { ++nslow; };
-#endif
   auto spill_add = [&](OT* out_row, long long gbin, double wv) { global_add(out_row, gbin, wv); note_slow(); };
   // general path of one sample: exact bins, then shared window / global spill / drop.
   // Returns the window bin when the caller should do the shared add itself, else -1.
@@ -600,7 +594,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
         // Non-uniform variable: table entry of cell c-1 = a bin at or below the sample's, then lut_steps
         // compare-and-advance steps; window spills leave as inline predicated global REDs.
         // software pipeline: the loads of the next half group are issued before the current one is classified (one
-        // 16-byte load per array and thread in flight was latency-bound: 30 % of the stall samples at the loads)
+        // 16-byte load per array and thread in flight was latency-bound: 30 % of the stall samples at the loads; measured
+        // 3.19 -> 3.13 ms on config 5)
         T xn[KMAX][2]; WT wn[2] = {WT(1), WT(1)};
         auto fetch = [&](long long gg) {
           if (gg < 2 * nvec) {
@@ -609,20 +604,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
             if constexpr (!CNT) load2(pw + head, gg, wn);
           }
         };
-#if XH_HALF_PIPE
         fetch(tid);
-#endif
         for (long long g = tid; g < 2 * nvec; g += nthr) {          // g counts half groups
           T xh[KMAX][2]; WT wh[2];
-#if !XH_HALF_PIPE
-          fetch(g);
-#endif
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) { xh[k][0] = xn[k][0]; xh[k][1] = xn[k][1]; }
           wh[0] = wn[0]; wh[1] = wn[1];
-#if XH_HALF_PIPE
           fetch(g + nthr);
-#endif
 #if XH_PREFETCH_DIST > 0
           {
             const long long gp = g + static_cast<long long>(XH_PREFETCH_DIST + 1) * nthr;      // half groups ahead of the register prefetch

@@ -9,6 +9,9 @@ e = np.linspace(-4, 4, 257)
 axis = None
 if kind.startswith("uniform"):
     x = DeviceArray.uniform((n,), np.float32, seed=13); y = DeviceArray.uniform((n,), np.float32, seed=14); e = np.linspace(0, 1, 257)
+elif kind == "cfg4":
+    x = DeviceArray.normal((1024, 720, 1440), np.float32, seed=6); y = DeviceArray.normal((1024, 720, 1440), np.float32, seed=7)
+    e = np.linspace(-4, 4, 101); axis = [1, 2]; n = 1024 * 720 * 1440
 elif kind == "rows":
     x = DeviceArray.normal((n // 100_000, 100_000), np.float32, seed=1); y = DeviceArray.normal((n // 100_000, 100_000), np.float32, seed=2)
     e = np.linspace(-4, 4, 129); axis = [1]
@@ -20,4 +23,4 @@ t = {}; ms = []
 for _ in range(calls + 2):
     core._bincount(*arrays, weights=w is not None, axis=axis, bins=[e, e], _timing=t)
     ms.append(t["kernel_ms"])
-print(f"{os.path.basename(os.environ.get('XHIST_B200_LIB', 'main')):28s} {kind:15s} n={n:.3g}  kernel_ms median {np.median(ms[2:]):.4f}  min {np.min(ms[2:]):.4f}")
+print(f"{os.path.basename(os.environ.get('XHIST_B200_LIB', 'main')):12s} XH_PREFETCH={os.environ.get('XH_PREFETCH', 'auto'):5s} {kind:15s} n={n:.3g}  kernel_ms median {np.median(ms[2:]):.4f}  min {np.min(ms[2:]):.4f}")

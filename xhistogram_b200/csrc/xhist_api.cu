@@ -495,7 +495,7 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
       p.per_cta = per;
       grid = static_cast<int>((total + per - 1) / per);
     }
-    p.fx_vbits = 24; p.w_dtype = XH_NONE; p.store_owned_rows = 0;
+    p.fx_vbits = 24; p.w_dtype = XH_NONE; p.store_owned_rows = 0; p.prefetch = 1;
     pl.need_window = false;
     pl.zero = (d->flags & XH_FLAG_NO_ZERO) ? Plan::ZERO_NONE : Plan::ZERO_ALL;
     pl.l.dtype = d->dtype; pl.l.w_dtype = 4; pl.l.grid = grid; pl.l.threads = XHK_THREADS; pl.l.smem_bytes = smem_pk; pl.l.stream = stream;
@@ -528,6 +528,10 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
     p.hist_capacity = pl.window_budget;
   } else {
     ctas_per_sm = 2; threads = XHK_THREADS / 2;
+  }
+  {
+    static const int forced = [] { const char* e = std::getenv("XH_PREFETCH"); return e ? std::atoi(e) : -1; }();    // A/B switch
+    p.prefetch = forced >= 0 ? (forced ? 1 : 0) : 1;
   }
   const long long total = p.M * p.N;
   int grid = c->sm_count * ctas_per_sm;

@@ -95,6 +95,8 @@ struct XhkParams {
   int tile_n;                       // samples of one real row
   unsigned tile_magic; int tile_shift;   // q = (umulhi(n, magic) + n) >> shift == n / tile_n for n < 2^31
   int fx_vbits;                     // fixed point: |v| < 2^fx_vbits keeps every per-flush bin sum below 2^63
+  int prefetch;                     // 1: L2 prefetch two iterations ahead (default; XH_PREFETCH=0 switches it off for A/B runs — same box,
+                                    //    config 4: 1.45 ms without, 1.42 with; config 2: 1.67 / 1.61; config 3: 2.25 / 1.99)
   int spilly;                       // host hint from the cached verdict: > 2 % of the samples left the fast path last time
   unsigned long long* stats;        // device counter: samples that left the fast path (window spills, weights outside the
                                     // fixed-point form) — lets the host notice a cached probe verdict that no longer fits

@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
           }
 #if XH_PREFETCH_DIST > 0
           const long long gp = gu + static_cast<long long>(XH_PREFETCH_DIST * U) * nthr;
-          if (gp < nvec) {
+          if (p.prefetch && gp < nvec) {
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) prefetch_l2(px[k] + head + 4 * gp);
           }
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 #if XH_PREFETCH_DIST > 0
           {
             const long long gp = g + static_cast<long long>(XH_PREFETCH_DIST + 1) * nthr;      // half groups ahead of the register prefetch
-            if (gp < 2 * nvec) {
+            if (p.prefetch && gp < 2 * nvec) {
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) prefetch_l2(px[k] + head + 2 * gp);
               if constexpr (!CNT) prefetch_l2(pw + head + 2 * gp);
@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_hist(const __grid_constant__
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const long long gp = g + static_cast<long long>(XH_PREFETCH_DIST * U) * nthr + static_cast<long long>(u) * ustride;
-            if (gp < nvec) {
+            if (p.prefetch && gp < nvec) {
 #pragma unroll
               for (int k = 0; k < KMAX; ++k) prefetch_l2(px[k] + head + 4 * gp);
               if constexpr (!CNT) prefetch_l2(pw + head + 4 * gp);

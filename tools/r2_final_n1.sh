@@ -5,5 +5,3 @@ timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_final_bench_n1.json 2> gpurun_out/r2_final_bench_n1.err
 tail -c 200 gpurun_out/r2_final_bench_n1.json; tail -2 gpurun_out/r2_final_bench_n1.err
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_final_bench_ref.json 2>/dev/null
-tail -c 300 gpurun_out/r2_final_bench_ref.json

@@ -300,6 +300,12 @@ int prep_var_i64(const int64_t* e, int E, int k, XhkParams& p, std::vector<long 
   return XH_OK;
 }
 
+// L2 prefetch in the vector loops: on, unless XH_PREFETCH=0 (A/B runs)
+int prefetch_default() {
+  static const int v = [] { const char* e = std::getenv("XH_PREFETCH"); return e ? (std::atoi(e) ? 1 : 0) : 1; }();
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------ plan + launch
 struct Plan {
   XhkParams p;
@@ -495,7 +501,7 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
       p.per_cta = per;
       grid = static_cast<int>((total + per - 1) / per);
     }
-    p.fx_vbits = 24; p.w_dtype = XH_NONE; p.store_owned_rows = 0; p.prefetch = 1;
+    p.fx_vbits = 24; p.w_dtype = XH_NONE; p.store_owned_rows = 0; p.prefetch = prefetch_default();
     pl.need_window = false;
     pl.zero = (d->flags & XH_FLAG_NO_ZERO) ? Plan::ZERO_NONE : Plan::ZERO_ALL;
     pl.l.dtype = d->dtype; pl.l.w_dtype = 4; pl.l.grid = grid; pl.l.threads = XHK_THREADS; pl.l.smem_bytes = smem_pk; pl.l.stream = stream;
@@ -529,10 +535,7 @@ int plan_block(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream, Pl
   } else {
     ctas_per_sm = 2; threads = XHK_THREADS / 2;
   }
-  {
-    static const int forced = [] { const char* e = std::getenv("XH_PREFETCH"); return e ? std::atoi(e) : -1; }();    // A/B switch
-    p.prefetch = forced >= 0 ? (forced ? 1 : 0) : 1;
-  }
+  p.prefetch = prefetch_default();
   const long long total = p.M * p.N;
   int grid = c->sm_count * ctas_per_sm;
   const long long min_per_cta = 4096;
@@ -807,7 +810,7 @@ int run_mw_device(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t stream,
   for (int k = 0; k < d->n_vars; ++k) { p.data[k] = d->data[k]; p.stride[k] = d->row_stride[k]; }
   p.w = d->weights; p.wstride = d->w_row_stride; p.out = d->out; p.edges = pr.dev_edges; p.w_dtype = d->w_dtype;
   p.lut = reinterpret_cast<const unsigned short*>(static_cast<const unsigned char*>(pr.dev_edges) + pr.lut_dev_off);
-  p.stats = c->dummy_stats;
+  p.stats = c->dummy_stats; p.prefetch = prefetch_default();
   XhkMultiWeights m = {};
   m.nw = d->n_weights; m.w[0] = d->weights;
   for (int q = 1; q < m.nw; ++q) m.w[q] = d->weights_more[q - 1];
@@ -955,7 +958,7 @@ int run_cols_device(Ctx* c, const Prep& pr, const xh_desc* d, cudaStream_t strea
   for (int k = 0; k < d->n_vars; ++k) p.data[k] = d->data[k];
   p.w = d->weights; p.out = d->out; p.edges = pr.dev_edges; p.w_dtype = d->w_dtype;
   p.lut = reinterpret_cast<const unsigned short*>(static_cast<const unsigned char*>(pr.dev_edges) + pr.lut_dev_off);
-  p.stats = c->dummy_stats;
+  p.stats = c->dummy_stats; p.prefetch = prefetch_default();
   const long long inner = d->n_inner, outer = d->n_rows / inner;
   const long long tiles = ((inner + tm - 1) / tm) * outer;
   int nsplit = 1;

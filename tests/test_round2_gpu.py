@@ -329,3 +329,33 @@ def test_packed_counts_guard_bit_carries(layout):
     with core.debug_flags(_cabi.XH_FLAG_FORCE_PACKED):
         got, _ = core.histogram(x, y, bins=[e, e2], axis=axis)
     assert np.array_equal(got, want)
+
+
+def test_call_plan_cache_is_revalidated():
+    """Repeat calls on the same DeviceArrays / edge arrays reuse the filled descriptor; edits to the edges, new data in the
+    buffers and new buffers must all be noticed."""
+    r = np.random.default_rng(70)
+    x = r.standard_normal(300_000).astype(np.float32)
+    w = r.random(300_000).astype(np.float32)
+    e = np.linspace(-4, 4, 65)
+    dx, dw = DeviceArray.from_numpy(x), DeviceArray.from_numpy(w)
+    for _ in range(3):
+        h, be = core.histogram(dx, bins=[e], weights=dw, density=True)
+        assert be[0] is e
+        assert_hist_equal(h, O.histogram(x, bins=e, weights=w, density=True)[0], rtol=1e-6)
+    e[1:-1] += 0.021                                    # same edge object, new content
+    for _ in range(2):
+        assert_hist_equal(core.histogram(dx, bins=[e], weights=dw, density=True)[0], O.histogram(x, bins=e, weights=w, density=True)[0], rtol=1e-6)
+    x2 = (x * 0.5 + 1).astype(np.float32)               # same buffers, new data
+    _cabi.check(_cabi.lib().xh_memcpy(0, dx.ptr, x2.ctypes.data, x2.nbytes, _cabi.XH_DEVICE, _cabi.XH_HOST), "h2d")
+    for _ in range(2):
+        assert_hist_equal(core.histogram(dx, bins=[e], weights=dw, density=True)[0], O.histogram(x2, bins=e, weights=w, density=True)[0], rtol=1e-6)
+    for _ in range(3):                                  # counts and rows through the same cache
+        assert np.array_equal(core.histogram(dx, bins=[e])[0], np.histogram(x2, bins=e)[0])
+    dr = dx.reshape(300, 1000)
+    for _ in range(3):
+        got, _ = core.histogram(dr, bins=[e], axis=1)
+        assert np.array_equal(got, np.stack([np.histogram(row, bins=e)[0] for row in x2.reshape(300, 1000)]))
+    dx.free()
+    with pytest.raises(Exception):
+        core.histogram(dx, bins=[e], weights=dw, density=True)      # a freed array is not served from the cache

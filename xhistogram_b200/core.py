@@ -689,11 +689,107 @@ def _upload_pays(args, weights, bins, range_):
     return all(a.dtype == a0.dtype for a in args) and total <= _UPLOAD_LIMIT_BYTES
 
 
+def M_N_of_rows(shape, ndim, full, axis):
+    """(M, N) when the reduced axes are all axes or the trailing ones (the row layout, read in place), else None."""
+    if full:
+        return 1, int(math.prod(shape))
+    ax = sorted(axis)
+    if ax == list(_range(ndim - len(ax), ndim)):
+        n = int(math.prod(shape[ndim - len(ax):]))
+        return int(math.prod(shape[: ndim - len(ax)])), n
+    return None
+
+
+# Repeat calls on the same DeviceArrays with the same edge arrays (a loop over time steps, a benchmark) skip the argument
+# handling altogether: the filled descriptor is kept, keyed by the identity of the arguments, and re-validated per call —
+# every array must still be the same live object with the same buffer, every edge array must still have the same CONTENT
+# (the content-keyed ``_edge_info`` cache returns the same record only then).  Anything else takes the full path.
+_plans = {}
+
+
+class _Plan:
+    __slots__ = ("refs", "ptrs", "bins", "infos", "desc", "shape_out", "odt", "MB", "keep")
+
+
+def _plan_lookup(key, all_arrays, bins):
+    plan = _plans.get(key)
+    if plan is None:
+        return None
+    for r, ptr, a in zip(plan.refs, plan.ptrs, all_arrays):
+        if r() is not a or a.ptr != ptr:
+            del _plans[key]
+            return None
+    for b, pb, info in zip(bins, plan.bins, plan.infos):
+        if b is not pb() or _edge_info(b) is not info:
+            del _plans[key]
+            return None
+    return plan
+
+
+def _plan_run(plan):
+    d = _cabi.XhDesc.from_buffer_copy(plan.desc)
+    out = result_pool.array(plan.MB, plan.odt)
+    if out is not None:
+        d.flags |= _cabi.XH_FLAG_OUT_PINNED
+        d.out = out.__array_interface__["data"][0]
+    else:
+        out = np.empty(plan.MB, dtype=plan.odt)
+        d.out = out.ctypes.data
+    rc = _cabi.lib().xh_hist(C.byref(d))
+    if rc:
+        _cabi.check(rc, "xh_hist")
+    return out.reshape(plan.shape_out)
+
+
+def _plan_store(key, all_arrays, bins, infos, views, n_args, M, N, shape_out, weighted, density_on_device, extra_flags=0):
+    import weakref
+    K = n_args
+    d = _cabi.XhDesc()
+    d.n_vars, d.dtype, d.mem, d.out_mem, d.device = K, _xh_dtype(views[0][2]), _cabi.XH_DEVICE, _cabi.XH_HOST, views[0][3]
+    d.w_dtype = _xh_dtype(views[K][2]) if weighted else _cabi.XH_NONE
+    d.flags = (_cabi.XH_FLAG_DENSITY if density_on_device else 0) | extra_flags
+    d.n_rows, d.n_cols = M, N
+    B = 1
+    for k in _range(K):
+        d.data[k] = views[k][0]
+        d.row_stride[k] = N
+        d.edges[k] = infos[k].ptr
+        d.n_edges[k] = infos[k].n
+        B *= infos[k].n - 1
+        if density_on_device:
+            d.widths[k] = infos[k].wptr
+            d.widths_f32[k] = infos[k].w_f32
+    if weighted:
+        d.weights = views[K][0]
+        d.w_row_stride = N
+    plan = _Plan()
+    plan.refs = [weakref.ref(a) for a in all_arrays]
+    plan.ptrs = [a.ptr for a in all_arrays]
+    plan.bins = [weakref.ref(b) for b in bins]
+    plan.infos = list(infos)
+    plan.desc = bytes(d)
+    plan.shape_out = shape_out
+    plan.odt = np.float64 if (weighted or density_on_device) else np.int64
+    plan.MB = (M, B)
+    plan.keep = None
+    if len(_plans) >= 64:
+        _plans.pop(next(iter(_plans)))
+    _plans[key] = plan
+
+
 def _histogram_device(args, bins, range, axis, weights, density, out):
     """``histogram`` for device-resident inputs (``DeviceArray`` / ``__cuda_array_interface__``): nothing but metadata
     is touched on the host.  With ``out`` (a float64/int64-sized ``DeviceArray``) the call only enqueues: the result
     stays in HBM and is valid in stream order (``xh_sync`` or any later library call orders after it)."""
     all_arrays = list(args) + ([weights] if weights is not None else [])
+    plan_key = None
+    if (out is None and range is None and _debug_flags == 0 and _timing_sink is None and isinstance(bins, (list, tuple))
+            and len(bins) == len(args) and all(type(a) is DeviceArray for a in all_arrays) and all(type(b) is np.ndarray for b in bins)):
+        plan_key = (tuple(id(a) for a in all_arrays), weights is not None, tuple(id(b) for b in bins),
+                    None if axis is None else tuple(np.atleast_1d(axis).tolist()), bool(density))
+        plan = _plan_lookup(plan_key, all_arrays, bins)
+        if plan is not None:
+            return _plan_run(plan), list(bins)
     if not all(is_device_array(a) for a in all_arrays):
         raise TypeError("cannot mix device-resident and host arrays in one call")
     views = [as_device_view(a) for a in all_arrays]
@@ -725,6 +821,9 @@ def _histogram_device(args, bins, range, axis, weights, density, out):
     if out is not None:
         return out.reshape(kept_shape + nbins), bins
     h = h.reshape(kept_shape + nbins)
+    if plan_key is not None and (not density or device_density) and M_N_of_rows(shape, ndim, full, axis) is not None and h.size:
+        M, N = M_N_of_rows(shape, ndim, full, axis)
+        _plan_store(plan_key, all_arrays, bins, infos, views, n_inputs, M, N, kept_shape + nbins, weights is not None, device_density)
     if density and not device_density:
         areas = functools.reduce(np.multiply.outer, [np.diff(b) for b in bins])
         sums = h.sum(axis=tuple(_range(-n_inputs, 0)), keepdims=True)

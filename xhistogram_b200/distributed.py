@@ -195,6 +195,17 @@ def histogram(*local_args, bins=None, range=None, axis=None, weights=None, densi
     over NVLink, density) and the result stays in HBM, valid in stream order.
     """
     comm = comm or Communicator()
+    # repeat call on the same device-resident shards and edge arrays: reuse the filled descriptor (core._plan_*)
+    plan_key = None
+    if (isinstance(comm, NcclCommunicator) and out is None and range is None and _core._debug_flags == 0 and _core._timing_sink is None
+            and isinstance(bins, (list, tuple)) and len(bins) == len(local_args) and all(type(b) is np.ndarray for b in bins)
+            and all(type(a) is _core.DeviceArray for a in list(local_args) + ([weights] if weights is not None else []))):
+        every = list(local_args) + ([weights] if weights is not None else [])
+        plan_key = ("dist", comm.device, tuple(id(a) for a in every), weights is not None, tuple(id(b) for b in bins),
+                    None if axis is None else tuple(np.atleast_1d(axis).tolist()), bool(density), int(sharded_axis))
+        plan = _core._plan_lookup(plan_key, every, bins)
+        if plan is not None:
+            return _core._plan_run(plan), list(bins)
     a0 = local_args[0]
     nd = np.ndim(a0) if not _core.is_device_array(a0) else len(_core.as_device_view(a0)[1])
     sharded_axis = sharded_axis if sharded_axis >= 0 else nd + sharded_axis
@@ -219,6 +230,16 @@ def histogram(*local_args, bins=None, range=None, axis=None, weights=None, densi
         if isinstance(comm, NcclCommunicator):
             # ONE native call: histogram kernels -> ncclAllReduce of the partials in HBM -> density -> D2H of the result
             h = _fused_allreduce(local_args, weights, edges, axis, nd, comm, density, out)
+            if plan_key is not None and h.size and all(e is b for e, b in zip(edges, bins)):
+                shape = _core.as_device_view(local_args[0])[1]
+                full = axis is None or set(red) == set(_range(nd))
+                mn = _core.M_N_of_rows(shape, nd, full, red)
+                on_device = (not density) or all(np.asarray(e).dtype in (np.float32, np.float64) for e in edges)
+                if mn is not None and on_device:
+                    every = list(local_args) + ([weights] if weights is not None else [])
+                    infos = [_core._edge_info(e) for e in edges]
+                    _core._plan_store(plan_key, every, edges, infos, [_core.as_device_view(a) for a in every], len(local_args), mn[0], mn[1],
+                                      h.shape, weights is not None, bool(density), _cabi.XH_FLAG_ALLREDUCE)
             return h, edges
         if out is not None:
             raise TypeError("out= needs an NcclCommunicator")

@@ -717,7 +717,8 @@ int plan_and_enqueue(Ctx* c, const PrepEntry& pe, const xh_desc* d, cudaStream_t
   // shared adds are cheaper than the packed form's returning ones (1.25 vs 1.77 ms per 1e9 samples on config 3), while every
   // per cent of spilled samples costs the windowed form about 0.7 ms.
   const bool forced = (d->flags & XH_FLAG_FORCE_PACKED) != 0;
-  if (d->w_dtype == XH_NONE && d->dtype != XH_I64 && pr.base.all_uniform && tile_rows == 1 && (pl.p.hist_mode == XHK_WINDOW || forced) &&
+  static const bool no_packed = std::getenv("XH_NO_PACKED") != nullptr;      // (profiling the windowed form on data that spills)
+  if (!no_packed && d->w_dtype == XH_NONE && d->dtype != XH_I64 && pr.base.all_uniform && tile_rows == 1 && (pl.p.hist_mode == XHK_WINDOW || forced) &&
       !(d->flags & (XH_FLAG_FORCE_GLOBAL | XH_FLAG_FORCE_WINDOW | XH_FLAG_FORCE_SEARCH))) {
     if (forced || (cache && verdict_slow_fraction(c, pe, d, tile_rows, tile_n, pl.window_budget, 0) > 0.005)) {
       Plan pk;

@@ -81,3 +81,38 @@ def test_shard_bounds_cover_everything():
             b = [shard_bounds(n, world, r) for r in range(world)]
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+
+
+def test_file_bootstrap_of_the_nccl_id(tmp_path, monkeypatch):
+    """NcclCommunicator.from_env: rank 0 publishes the id through a file, the other ranks read exactly those 128 bytes
+    (the NCCL calls themselves are stubbed: no GPU here)."""
+    from xhistogram_b200 import distributed as D
+
+    got = {}
+
+    def fake_init(self, device, rank, world, unique_id):
+        self.device, self.rank, self.world = device, rank, world
+        got[rank] = bytes(unique_id)
+
+    uid = bytes(range(128))
+    monkeypatch.setattr(D.NcclCommunicator, "__init__", fake_init)
+    monkeypatch.setattr(D.NcclCommunicator, "create_unique_id", staticmethod(lambda: uid))
+    path = str(tmp_path / "id")
+    monkeypatch.setenv("XHIST_NCCL_ID_FILE", path)
+    monkeypatch.setenv("WORLD_SIZE", "3")
+
+    def from_env_as(rank, timeout=20.0):
+        monkeypatch.setenv("RANK", str(rank))
+        monkeypatch.setenv("LOCAL_RANK", str(rank))
+        return D.NcclCommunicator.from_env(timeout=timeout)
+
+    c0 = from_env_as(0)                             # publishes; with __init__ stubbed it returns (and removes the file) at once
+    assert c0.rank == 0 and got[0] == uid and not os.path.exists(path)
+    with open(path, "wb") as f:                     # what a still-joining rank 0 leaves for the others
+        f.write(uid)
+    c1 = from_env_as(1)
+    assert c1.rank == 1 and c1.world == 3 and c1.device == 1 and got[1] == uid
+    with open(path, "wb") as f:                     # a truncated file is not accepted
+        f.write(uid[:50])
+    with pytest.raises(TimeoutError):
+        from_env_as(2, timeout=0.3)

@@ -1558,7 +1558,23 @@ int xh_comm_allreduce(int device, void* dev_buf, int64_t count, int dtype_is_f64
 int xh_comm_destroy(int device) {
   Ctx* c; int rc = get_ctx(device, &c); if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
-  if (c->comm) { CU(cudaSetDevice(c->device)); cudaDeviceSynchronize(); peer_release(c); c->peer.state = 0; NC(g_nccl.CommDestroy(c->comm)); c->comm = nullptr; c->comm_ranks = 0; }
+  if (c->comm) {
+    CU(cudaSetDevice(c->device));
+    cudaDeviceSynchronize();
+    if (c->peer.state == 1) {
+      // peers map this rank's symmetric buffer: release it only when every rank has finished its own kernels and arrived here
+      // (a collective, like ncclCommDestroy itself)
+      int* flag = nullptr;
+      if (cudaMalloc(&flag, sizeof(int)) == cudaSuccess) {
+        cudaMemsetAsync(flag, 0, sizeof(int), c->stream);
+        g_nccl.AllReduce(flag, flag, 1, kNcclInt32, kNcclSum, c->comm, c->stream);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(flag);
+      }
+    }
+    peer_release(c); c->peer.state = 0;
+    NC(g_nccl.CommDestroy(c->comm)); c->comm = nullptr; c->comm_ranks = 0;
+  }
   return XH_OK;
 }
 

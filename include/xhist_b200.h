@@ -52,6 +52,9 @@ typedef enum xh_mem { XH_HOST = 0, XH_DEVICE = 1 } xh_mem;
 #define XH_FLAG_FORCE_SEARCH 4u /* testing: bypass the uniform-edge fast path, binary search only           */
 #define XH_FLAG_FORCE_WINDOW 8u /* testing: use the windowed shared-memory histogram even if all bins fit   */
 #define XH_FLAG_FORCE_PACKED 512u /* testing: counts take the packed 16-bit shared histogram whenever it applies            */
+#define XH_FLAG_ONE_PASS 1024u  /* several weight arrays on DEVICE data: take the one-pass kernel (k_hist_mw) although one fused pass
+                                   per weight array is faster there (what the library does by default; host data always take the
+                                   one-pass kernel — the samples cross PCIe once)                                              */
 #define XH_FLAG_NO_FX32 16u     /* testing: fp32 weights never take the one-limb (4 bytes per bin) accumulation  */
 #define XH_FLAG_ALLREDUCE 64u   /* sum the (n_rows, bins) result over the ranks of this device's communicator
                                    (xh_comm_init_rank) with ncclAllReduce before the density / the copy to `out`:
@@ -114,7 +117,7 @@ typedef struct xh_desc {
   int32_t widths_f32[XH_MAX_VARS];    /* 1: numpy holds these widths as float32 (a product of two such is
                                          rounded to float32, as np.multiply.outer does in core.py:447-454)      */
   int32_t n_weights;                  /* 0 / 1: `weights` alone.  2..XH_MAX_WEIGHTS: several weight arrays over the same samples
-                                         in ONE pass (the reference needs one call per weight array: tutorial.ipynb:298-360,
+                                         in ONE call (the reference needs one call per weight array: tutorial.ipynb:298-360,
                                          "TODO: allow list of weights" xarray.py:106): weights, weights_more[0..n_weights-2], all
                                          of w_dtype and addressed with w_row_stride; out is (n_weights, n_rows, bins) float64   */
   int32_t reserved2;

@@ -249,10 +249,14 @@ def test_nccl_minmax_and_file_bootstrap_single_rank(tmp_path, monkeypatch):
         comm.close()
 
 
-@pytest.mark.parametrize("where", ["host", "device"])
+@pytest.mark.parametrize("where", ["host", "device", "device_one_pass"])
 @pytest.mark.parametrize("case", ["flat_2d_fits", "rows", "flat_big_bins", "f64_three_weights"])
 def test_list_of_weights_one_pass(where, case):
-    """weights=[w1, w2, ...]: one pass, one histogram per weight array; equals separate oracle calls."""
+    """weights=[w1, w2, ...]: one call, one histogram per weight array; equals separate oracle calls.  Host inputs take the
+    one-pass kernel (k_hist_mw), device-resident inputs one fused pass per weight array (faster there) unless
+    XH_FLAG_ONE_PASS asks for k_hist_mw."""
+    import contextlib
+
     r = np.random.default_rng(50)
     if case == "flat_2d_fits":
         shape, edges, wdt, nw, axis = (1_000_003,), [np.linspace(-3, 3, 101), np.linspace(-3, 3, 81)], np.float32, 2, None
@@ -266,10 +270,16 @@ def test_list_of_weights_one_pass(where, case):
     args = [r.standard_normal(shape).astype(ddt) for _ in edges]
     ws = [r.standard_normal(shape).astype(wdt) for _ in range(nw)]
     ws[0][...] = 1.0                                             # plane 0 = the counts, as floats
-    if where == "device":
+    if where != "host":
         a_in, w_in = [DeviceArray.from_numpy(a) for a in args], [DeviceArray.from_numpy(w) for w in ws]
     else:
         a_in, w_in = args, ws
+    forced = core.debug_flags(_cabi.XH_FLAG_ONE_PASS) if where == "device_one_pass" else contextlib.nullcontext()
+    with forced:
+        _check_weight_list(a_in, w_in, args, ws, edges, axis, nw)
+
+
+def _check_weight_list(a_in, w_in, args, ws, edges, axis, nw):
     h, _ = core.histogram(*a_in, bins=edges, axis=axis, weights=w_in)
     assert h.shape[0] == nw
     for q in range(nw):

@@ -25,6 +25,7 @@ XH_FLAG_ALLREDUCE = 64
 XH_FLAG_ASYNC = 128
 XH_FLAG_OUT_PINNED = 256
 XH_FLAG_FORCE_PACKED = 512
+XH_FLAG_ONE_PASS = 1024
 XH_NCCL_UNIQUE_ID_BYTES = 128
 
 _ERRORS = {

@@ -587,11 +587,12 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
 # public entry point (reference: core.py:250-466)
 # --------------------------------------------------------------------------------------------
 def _histogram_weight_list(args, bins, range, axis, weights, density):
-    """``weights=[w1, w2, ...]``: histograms of the SAME samples under several weight arrays in one pass over the data
+    """``weights=[w1, w2, ...]``: histograms of the SAME samples under several weight arrays in one call
     (the reference needs one call per weight array — e.g. the weighted mean of its tutorial, histogram(weights=w*a) /
-    histogram(weights=w), tutorial.ipynb:298-360; "TODO: allow list of weights", xarray.py:106).  The samples are read
-    and classified once; ``hist`` gains a leading axis of length ``len(weights)``.  Host or device-resident inputs;
-    device-resident inputs must reduce all or the trailing axes."""
+    histogram(weights=w), tutorial.ipynb:298-360; "TODO: allow list of weights", xarray.py:106).  ``hist`` gains a
+    leading axis of length ``len(weights)``.  Host inputs are read, moved over PCIe and classified ONCE (``k_hist_mw``);
+    for device-resident inputs the library runs one fused pass per weight array, which is faster there (see
+    ``XH_FLAG_ONE_PASS`` in ``include/xhist_b200.h``).  Device-resident inputs must reduce all or the trailing axes."""
     nw = len(weights)
     if not 2 <= nw <= _cabi.XH_MAX_WEIGHTS:
         raise ValueError(f"a list of weights takes 2 to {_cabi.XH_MAX_WEIGHTS} arrays")

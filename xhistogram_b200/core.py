@@ -529,7 +529,7 @@ def _desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device
         if mem == _cabi.XH_HOST and not w.size:
             d.w_dtype = _cabi.XH_NONE
     nw = 1
-    if w_more:                                            # several weight arrays over the same samples, one pass
+    if w_more:                                            # several weight arrays over the same samples, one call
         nw = 1 + len(w_more)
         d.n_weights = nw
         for q, wq in enumerate(w_more):
@@ -837,7 +837,7 @@ def histogram(*args, bins=None, range=None, axis=None, weights=None, density=Fal
     """Histogram applied along specified axis / axes — signature of ``xhistogram.core.histogram``.
 
     Parameters are those of the reference (see its docstring, core.py:259-333).  Extensions, all optional:
-    ``weights`` may be a list of 2-4 arrays: one pass over the samples, ``hist`` gains a leading axis (one histogram per
+    ``weights`` may be a list of 2-4 arrays: one call for all of them, ``hist`` gains a leading axis (one histogram per
     weight array; see ``_histogram_weight_list``);
     ``devices`` — list of CUDA ordinals to shard a host-resident request over (rows are split when enough rows are
     kept, otherwise the reduced axis is split and the partial histograms are summed with NCCL);

@@ -58,6 +58,8 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
+    PERIOD_MS = os.environ.get("XH_BENCH_SMI_MS", "50")
+
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
         self.proc = None
@@ -66,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", self.PERIOD_MS,
                                           "-i", str(self.gpu_index)], stdout=fd, stderr=subprocess.DEVNULL)
             os.close(fd)
         except Exception:
@@ -331,18 +333,21 @@ def main():
     w = DeviceArray.uniform((n,), np.float32, seed=SEEDS[2], offset=off, device=dev)
     bins = [EDGES, EDGES]
 
-    def timed_steps(fn, steps, warmup):
+    def timed_steps(fn, steps, warmup, after_warmup=None):
         """W warm-ups, then exactly K steps between barriers; CUDA events on the library stream and the host clock,
         max over ranks.  Returns (ms per step, last result)."""
+        last = None
         for _ in range(warmup):
-            fn()
+            last = fn()        # (kept while the next call runs, as in the timed loop: the result pool reaches its steady-state size —
+                               # page-locking one more 512 KB block costs 4-15 ms — during the warm-up, not in timed step 2)
+        if after_warmup is not None:
+            after_warmup()
         gc.collect()
         gc.disable()          # (as timeit does: a generation-2 collection inside a 5-step region costs several steps)
         try:
             barrier()
             _cabi.check(lib.xh_timer_start(dev), "timer")
             t0 = time.perf_counter()
-            last = None
             trace = [] if os.environ.get("XH_BENCH_TRACE") else None
             for _ in range(steps):
                 if trace is not None:
@@ -402,11 +407,10 @@ def main():
     if rank == 0:
         sampler.start()
         sampler.wait_ready()
-    for _ in range(args.warmup):
-        step_device()
-    if comm is None:
-        core._timing_sink = kernel_ms      # every timed step reports the device time of its kernels (library-stream events)
-    ms_per_step, h_last = timed_steps(step_device, args.steps, 0)
+    def sink_on():
+        if comm is None:
+            core._timing_sink = kernel_ms  # every TIMED step reports the device time of its kernels (library-stream events)
+    ms_per_step, h_last = timed_steps(step_device, args.steps, args.warmup, sink_on)
     core._timing_sink = None
     value = world * n / (ms_per_step * 1e-3)
 
@@ -459,7 +463,8 @@ def main():
             return core.histogram(hx.array, hy.array, bins=bins, weights=hw.array, density=True)[0]
         return D.histogram(hx.array, hy.array, bins=bins, weights=hw.array, density=True, comm=comm, sharded_axis=0)[0]
 
-    step_e2e()
+    h_e2e = step_e2e()
+    h_e2e = step_e2e()            # (the second warm-up call runs while the first result is held, as every timed step does)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

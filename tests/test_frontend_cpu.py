@@ -167,3 +167,53 @@ def test_integer_and_bool_data(patched):
     with pytest.raises(TypeError):
         core.histogram(big, bins=np.array([0.0, 2.0**61]))             # float edges: the float64 cast would be lossy
     assert core.histogram(big, bins=np.array([0, 2**61]))[0].tolist() == [1]   # integer edges: exact int64 path
+
+
+def test_result_pool_slabs_and_recycling(monkeypatch):
+    """device.ResultPool without CUDA (the page-locking call replaced by a plain allocator): a miss takes a slab of 4, 8,
+    16, ... blocks in ONE allocation, blocks are disjoint, recycled when the result array dies, and the byte limit holds."""
+    import ctypes as C
+    import gc
+
+    from xhistogram_b200 import device as dev_mod
+
+    calls, keep = [], []
+
+    class FakeLib:
+        @staticmethod
+        def xh_host_alloc(nbytes, pp):
+            buf = C.create_string_buffer(nbytes)
+            keep.append(buf)
+            calls.append(nbytes)
+            C.cast(pp, C.POINTER(C.c_void_p))[0] = C.addressof(buf)
+            return 0
+
+    monkeypatch.setattr(dev_mod._cabi, "lib", lambda: FakeLib)
+    pool = dev_mod.ResultPool(limit=40 << 20, largest=8 << 20)
+    cap = 1 << 19                                                   # size class of a 256 x 256 float64 result
+    held = [pool.array((256, 256), np.float64) for _ in range(4)]
+    assert calls == [4 * cap]                                       # one allocation served four results
+    addrs = [a.__array_interface__["data"][0] for a in held]
+    assert len(set(addrs)) == 4 and max(addrs) - min(addrs) == 3 * cap
+    for i, a in enumerate(held):
+        a[...] = i                                                  # disjoint, writable
+    assert [float(a[0, 0]) for a in held] == [0.0, 1.0, 2.0, 3.0]
+    held.append(pool.array((65536,), np.int64))                     # same class, pool empty: the next slab has 8 blocks
+    assert calls == [4 * cap, 8 * cap]
+    first = held[0].__array_interface__["data"][0]
+    view = held[0][:10]                                             # a view keeps the block lent
+    held[0] = None
+    gc.collect()
+    assert first not in pool.free[cap]
+    del view
+    gc.collect()
+    assert first in pool.free[cap]
+    n_alloc = len(calls)
+    for _ in range(50):                                             # steady state of a loop that keeps the previous result
+        held[1] = pool.array((256, 256), np.float64)
+    assert len(calls) == n_alloc
+    assert pool.array((3, 5), np.float64).shape == (3, 5) and calls[-1] == 4 * (1 << 16)      # smallest class: 64 KB blocks
+    assert pool.array((2 << 20,), np.float64) is None               # above `largest`: the caller falls back to a pageable array
+    assert pool.array((0, 7), np.float64) is None
+    big = [pool.array((1 << 20,), np.float64) for _ in range(8)]    # 8 MB blocks against the 40 MB limit
+    assert sum(b is not None for b in big) >= 1 and pool.total <= pool.limit and big[-1] is None

@@ -369,3 +369,27 @@ def test_call_plan_cache_is_revalidated():
     dx.free()
     with pytest.raises(Exception):
         core.histogram(dx, bins=[e], weights=dw, density=True)      # a freed array is not served from the cache
+
+
+def test_kept_results_do_not_alias():
+    """Results are returned in pinned blocks cut from slabs (device.ResultPool): a caller who keeps many of them must find
+    every one intact after later calls wrote theirs (counts, weighted, density; host and device inputs)."""
+    r = np.random.default_rng(77)
+    e = np.linspace(-3, 3, 129)
+    kept, want = [], []
+    for i in range(14):
+        x = (r.standard_normal(200_000) + 0.1 * i).astype(np.float32)
+        y = r.standard_normal(200_000).astype(np.float32)
+        w = r.random(200_000).astype(np.float32)
+        kw = [dict(), dict(weights=w), dict(weights=w, density=True)][i % 3]
+        if i % 2:
+            dx, dy = DeviceArray.from_numpy(x), DeviceArray.from_numpy(y)
+            dkw = {k: (DeviceArray.from_numpy(v) if k == "weights" else v) for k, v in kw.items()}
+            kept.append(core.histogram(dx, dy, bins=[e, e], **dkw)[0])
+        else:
+            kept.append(core.histogram(x, y, bins=[e, e], **kw)[0])
+        want.append(O.histogram(x, y, bins=[e, e], **kw)[0])
+    addrs = [h.__array_interface__["data"][0] for h in kept]
+    assert len(set(addrs)) == len(addrs)
+    for h, wnt in zip(kept, want):
+        assert_hist_equal(h, wnt, rtol=1e-6)

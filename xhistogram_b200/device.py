@@ -165,6 +165,7 @@ class ResultPool:
         self.limit, self.largest = limit, largest
         self.free = {}
         self.total = 0
+        self._slab = {}          # size class -> blocks in its next slab
 
     def array(self, shape, dtype):
         dtype = np.dtype(dtype)
@@ -176,23 +177,20 @@ class ResultPool:
         if lst:
             ptr = lst.pop()
         else:
-            # page-locking is slow (about 10 ms for 2 MB): the first miss of a size class takes a few blocks at once, so that a
-            # caller who keeps the previous result while asking for the next one does not pay it again in steady state
-            ptr = None
-            for _ in range(1 if cap in self.free else 3):
-                if self.total + cap > self.limit:
-                    break
-                p = C.c_void_p()
-                if _cabi.lib().xh_host_alloc(cap, C.byref(p)) != 0:
-                    break
-                self.total += cap
-                if ptr is None:
-                    ptr = p.value
-                else:
-                    self.free.setdefault(cap, []).append(p.value)
-            self.free.setdefault(cap, [])
-            if ptr is None:
+            # Page-locking is slow (4-15 ms per allocation, whatever its size), so a miss takes a SLAB of blocks in one
+            # allocation — 4 blocks the first time, twice as many on every later miss of the class: a caller who keeps the
+            # previous result while asking for the next one never pays it in steady state, and one who keeps every result
+            # (a list of histograms) pays it O(log n) times.  Slabs are never given back (process lifetime).
+            n = min(self._slab.get(cap, 4), (self.limit - self.total) // cap)
+            if n < 1:
                 return None
+            p = C.c_void_p()
+            if _cabi.lib().xh_host_alloc(n * cap, C.byref(p)) != 0:
+                return None
+            self.total += n * cap
+            self._slab[cap] = min(2 * n, 64)
+            ptr = p.value
+            self.free.setdefault(cap, []).extend(ptr + i * cap for i in range(n - 1, 0, -1))
         return np.asarray(_ResultBlock(self, ptr, cap, tuple(shape), dtype.str))
 
     def _give(self, ptr, cap):

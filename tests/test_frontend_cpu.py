@@ -13,7 +13,7 @@ from xhistogram_b200 import core
 
 
 def _oracle_desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem, device, devices, flags, timing,
-                      out_device=None, n_inner=0, density_widths=None):
+                      out_device=None, n_inner=0, density_widths=None, infos=None, w_more=None):
     def full(a, stride):
         a = np.asarray(a)
         if n_inner > 1:   # column layout: (outer, N, inner) C-contiguous -> logical rows a*inner + m
@@ -37,6 +37,10 @@ def _oracle_desc_call(arrs, strides, w, wstride, bins, M, N, dtype, wdtype, mem,
     ww = None if w is None else full(w, wstride)
     B = int(np.prod([len(b) - 1 for b in bins]))
     h = O.block_bincount(data, edges, ww).reshape(M, B)
+    if w_more:                         # several weight arrays over the same samples: planes (n_weights, M, B), as xh_hist returns them
+        assert density_widths is None
+        planes = [h.astype(np.float64)] + [O.block_bincount(data, edges, full(wq, wstride)).reshape(M, B).astype(np.float64) for wq in w_more]
+        return np.concatenate(planes, axis=0)
     if density_widths is not None:     # what k_density does on the device (core.py:444-462)
         import functools
         areas = functools.reduce(np.multiply.outer, density_widths).reshape(1, B)
@@ -217,3 +221,32 @@ def test_result_pool_slabs_and_recycling(monkeypatch):
     assert pool.array((0, 7), np.float64) is None
     big = [pool.array((1 << 20,), np.float64) for _ in range(8)]    # 8 MB blocks against the 40 MB limit
     assert sum(b is not None for b in big) >= 1 and pool.total <= pool.limit and big[-1] is None
+
+
+@pytest.mark.parametrize("axis", [None, 1, (0, 2), -1])
+@pytest.mark.parametrize("density", [False, True])
+def test_list_of_weights_host_logic(patched, axis, density):
+    """weights=[w1, w2, w3] (host inputs): broadcasting of the weight arrays, axis handling, planes -> leading axis, density per
+    plane — equal to one oracle call per weight array."""
+    r = np.random.default_rng(8)
+    x, y = r.standard_normal((3, 4, 50)), r.standard_normal((3, 4, 50))
+    ws = [r.random((3, 4, 50)), r.random((1, 4, 50)), np.full((3, 4, 50), 2.0)]          # (one of them broadcasts along axis 0)
+    bins = [np.linspace(-3, 3, 9), np.linspace(-3, 3, 6)]
+    h, edges = core.histogram(x, y, bins=bins, axis=axis, weights=ws, density=density)
+    assert h.shape[0] == 3 and all(np.array_equal(e, b) for e, b in zip(edges, bins))
+    for q, wq in enumerate(ws):
+        want, _ = O.histogram(x, y, bins=bins, axis=axis, weights=np.broadcast_to(wq, x.shape), density=density)
+        assert h[q].shape == want.shape
+        assert_hist_equal(h[q], want, rtol=1e-12)
+
+
+def test_list_of_weights_argument_errors(patched):
+    x = np.zeros(10)
+    with pytest.raises(ValueError, match="2 to"):
+        core.histogram(x, bins=4, range=(0, 1), weights=[np.ones(10)])
+    with pytest.raises(ValueError, match="2 to"):
+        core.histogram(x, bins=4, range=(0, 1), weights=[np.ones(10)] * 5)
+    with pytest.raises(TypeError, match="out= or devices="):
+        core.histogram(x, bins=4, range=(0, 1), weights=[np.ones(10)] * 2, devices=[0])
+    with pytest.raises(TypeError, match="string bin"):
+        core.histogram(x, bins="auto", weights=[np.ones(10)] * 2)

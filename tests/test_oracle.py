@@ -69,3 +69,50 @@ def test_oracle_thread_slabs_equal_single_slab():
     one = O.block_bincount([a, b], e)
     for t in (2, 3, 8):
         assert np.array_equal(O.block_bincount_threads([a, b], e, threads=t), one)
+
+
+def test_oracle_property_against_numpy_and_the_live_reference():
+    """Randomised (hypothesis): K = 1..3 variables, float32 / float64, non-uniform edges, samples planted exactly on edges,
+    next to them, NaN and +-inf, optional weights, every axis choice — the oracle equals np.histogramdd per kept row (what the
+    reference's own tests assert against) and, when the reference is mounted, the reference itself bit for bit."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    ref = load_reference_core() if reference_available() else None
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(seed=st.integers(0, 2**31 - 1), k=st.integers(1, 3), f32=st.booleans(), weighted=st.booleans(), rows=st.integers(1, 4),
+           n=st.integers(1, 200))
+    def check(seed, k, f32, weighted, rows, n):
+        r = np.random.default_rng(seed)
+        dt = np.float32 if f32 else np.float64
+        edges = [np.unique(np.round(r.uniform(-2, 2, int(r.integers(2, 9))), 2)) for _ in range(k)]
+        edges = [e if len(e) >= 2 else np.array([-1.0, 1.0]) for e in edges]
+        args = []
+        for e in edges:
+            a = r.normal(0, 1.5, (rows, n))
+            m = r.random((rows, n))
+            on = r.choice(e, (rows, n))
+            a = np.where(m < 0.15, on, a)                                              # exactly on an edge
+            a = np.where((m >= 0.15) & (m < 0.2), np.nextafter(on, np.inf), a)          # one ulp (float64) above
+            a = np.where((m >= 0.2) & (m < 0.23), np.nan, a)
+            a = np.where((m >= 0.23) & (m < 0.25), np.inf * np.sign(a), a)
+            args.append(a.astype(dt))
+        w = r.random((rows, n)).astype(dt) if weighted else None
+        h, _ = O.histogram(*args, bins=edges, axis=1, weights=w)
+        want = O.numpy_histogramdd_rows(args, edges, w)
+        assert h.shape == (rows,) + tuple(len(e) - 1 for e in edges)
+        if weighted:
+            assert_hist_equal(h.reshape(rows, -1), want.reshape(rows, -1), rtol=1e-12)
+        else:
+            assert np.array_equal(h.reshape(rows, -1), want.reshape(rows, -1))
+        if ref is not None:
+            h_ref, _ = ref.histogram(*args, bins=edges, axis=1, weights=w, block_size=None)
+            assert h.dtype == h_ref.dtype and np.array_equal(h, h_ref, equal_nan=True)
+        flat, _ = O.histogram(*args, bins=edges, weights=w)                            # all axes reduced = sum of the rows
+        if weighted:
+            np.testing.assert_allclose(flat, h.sum(axis=0), rtol=1e-12, atol=1e-300)
+        else:
+            assert np.array_equal(flat, h.sum(axis=0))
+
+    check()
